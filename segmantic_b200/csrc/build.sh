@@ -1,0 +1,20 @@
+#!/bin/bash
+# Builds segmantic_b200/libsegmantic_b200.so for sm_100a (B200) in-tree.
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+OUT="$HERE/../libsegmantic_b200.so"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+FLAGS=(-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC
+       -Xcompiler -fvisibility=hidden)
+mkdir -p "$HERE/build"
+OBJS=()
+for src in "$HERE"/*.cu; do
+  obj="$HERE/build/$(basename "${src%.cu}").o"
+  if [[ ! -f "$obj" || "$src" -nt "$obj" || "$HERE/common.cuh" -nt "$obj" || "$HERE/../../include/segmantic_b200.h" -nt "$obj" ]]; then
+    "$NVCC" "${FLAGS[@]}" ${SGM_PTXAS_V:+-Xptxas -v} -c "$src" -o "$obj" &
+  fi
+  OBJS+=("$obj")
+done
+wait
+"$NVCC" -shared -gencode arch=compute_100a,code=sm_100a -o "$OUT" "${OBJS[@]}"
+echo "built $OUT"

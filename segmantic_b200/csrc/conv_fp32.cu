@@ -1,0 +1,329 @@
+// fp32 CUDA-core convolution family: the `precision="fp32"` path (reference default numerics:
+// the reference runs fp32 always, seg/monai_unet.py:551-670) and the on-device cross-check for the
+// tcgen05 bf16 family.  Direct (gather-form) convolution over CG8 activations, FFMA accumulate.
+//
+//   conv_fp32_kernel   k in {1,3}^3, stride in {1,2}^3, zero padding k/2 at the WINDOW border
+//                      (each ROI window is convolved in isolation, as MONAI does).
+//                      IN_PLANAR: the stem reads window n straight from the planar volume.
+//                      OUT_BLEND / OUT_PLANAR: the head writes importance-weighted logits into the
+//                      volume accumulator / plain planar logits.
+//   convT_fp32_kernel  ConvTranspose k3 s2 p1 op1 as 8 output-parity classes per input voxel
+//                      (1,2,2,2,4,4,4,8 taps), input = channel concat of two tensors (the skip
+//                      connection's torch.cat is never materialised).
+#include "common.cuh"
+
+namespace sgm {
+
+namespace {
+
+constexpr int CO_T = 16;   // couts per thread, conv
+constexpr int CO_TT = 8;   // couts per thread, transposed conv
+constexpr int PT = 2;      // output positions per thread (along d0), conv
+
+__device__ __forceinline__ float prelu(float v, float alpha) { return v > 0.f ? v : alpha * v; }
+
+template <bool IN_PLANAR, int OUT_KIND>
+__global__ void __launch_bounds__(128) conv_fp32_kernel(const ConvArgs a) {
+  __shared__ __align__(16) float wsm[27 * 8 * CO_T];
+  const int tid = threadIdx.x;
+  const int t2 = tid & 7, t1 = (tid >> 3) & 3, t0 = tid >> 5;
+  const int nt2 = (a.od[2] + 7) >> 3, nt1 = (a.od[1] + 3) >> 2;
+  int tile = blockIdx.x;
+  const int b2 = tile % nt2;
+  tile /= nt2;
+  const int b1 = tile % nt1;
+  const int b0 = tile / nt1;
+  const int o2 = b2 * 8 + t2, o1 = b1 * 4 + t1;
+  int o0[PT];
+  bool ovalid[PT];
+#pragma unroll
+  for (int p = 0; p < PT; ++p) {
+    o0[p] = b0 * (4 * PT) + t0 + 4 * p;
+    ovalid[p] = o0[p] < a.od[0] && o1 < a.od[1] && o2 < a.od[2];
+  }
+  const int n = blockIdx.z, coblk = blockIdx.y;
+  const int ntaps = a.k[0] * a.k[1] * a.k[2];
+  const int cgin = a.cg0 + a.cg1;
+  const long long ivox = (long long)a.id[0] * a.id[1] * a.id[2];
+
+  float acc[PT][CO_T];
+#pragma unroll
+  for (int p = 0; p < PT; ++p)
+#pragma unroll
+    for (int c = 0; c < CO_T; ++c) acc[p][c] = 0.f;
+
+  int worg[3] = {0, 0, 0};
+  if (IN_PLANAR) {
+    worg[0] = a.win_origin[n * 3 + 0];
+    worg[1] = a.win_origin[n * 3 + 1];
+    worg[2] = a.win_origin[n * 3 + 2];
+  }
+
+  for (int cg = 0; cg < cgin; ++cg) {
+    const float4* wsrc =
+        reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.w) +
+                                        ((size_t)(coblk * cgin + cg) * ntaps * 8 * CO_T));
+    for (int i = tid; i < ntaps * 8 * CO_T / 4; i += 128) reinterpret_cast<float4*>(wsm)[i] = wsrc[i];
+    __syncthreads();
+    const float* src = nullptr;
+    if (!IN_PLANAR) {
+      src = (cg < a.cg0)
+                ? reinterpret_cast<const float*>(a.in0) + ((long long)n * a.cg0 + cg) * ivox * 8
+                : reinterpret_cast<const float*>(a.in1) + ((long long)n * a.cg1 + (cg - a.cg0)) * ivox * 8;
+    }
+    int tap = 0;
+    for (int k0 = 0; k0 < a.k[0]; ++k0)
+      for (int k1 = 0; k1 < a.k[1]; ++k1)
+        for (int k2 = 0; k2 < a.k[2]; ++k2, ++tap) {
+          const int i1 = o1 * a.s[1] + k1 - a.pad[1];
+          const int i2 = o2 * a.s[2] + k2 - a.pad[2];
+          const bool v12 = i1 >= 0 && i1 < a.id[1] && i2 >= 0 && i2 < a.id[2];
+          float x[PT][8];
+#pragma unroll
+          for (int p = 0; p < PT; ++p) {
+            const int i0 = o0[p] * a.s[0] + k0 - a.pad[0];
+            const bool v = ovalid[p] && v12 && i0 >= 0 && i0 < a.id[0];
+            if (IN_PLANAR) {
+#pragma unroll
+              for (int ci = 0; ci < 8; ++ci) x[p][ci] = 0.f;
+              if (v) {
+                const long long off =
+                    ((long long)(worg[0] + i0) * a.vd1 + (worg[1] + i1)) * a.vd2 + (worg[2] + i2);
+                const float* vol = reinterpret_cast<const float*>(a.in0);
+                for (int ci = 0; ci < 8; ++ci) {
+                  const int c = cg * 8 + ci;
+                  if (c < a.cin_real) x[p][ci] = __ldg(vol + c * a.vol_cstride + off);
+                }
+              }
+            } else {
+              float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+              if (v) {
+                const float4* ptr = reinterpret_cast<const float4*>(
+                    src + (((long long)i0 * a.id[1] + i1) * a.id[2] + i2) * 8);
+                lo = __ldg(ptr);
+                hi = __ldg(ptr + 1);
+              }
+              x[p][0] = lo.x, x[p][1] = lo.y, x[p][2] = lo.z, x[p][3] = lo.w;
+              x[p][4] = hi.x, x[p][5] = hi.y, x[p][6] = hi.z, x[p][7] = hi.w;
+            }
+          }
+          const float* wt = wsm + tap * 8 * CO_T;
+#pragma unroll
+          for (int ci = 0; ci < 8; ++ci) {
+#pragma unroll
+            for (int c4 = 0; c4 < CO_T / 4; ++c4) {
+              const float4 w = *reinterpret_cast<const float4*>(wt + ci * CO_T + c4 * 4);
+#pragma unroll
+              for (int p = 0; p < PT; ++p) {
+                acc[p][c4 * 4 + 0] = fmaf(x[p][ci], w.x, acc[p][c4 * 4 + 0]);
+                acc[p][c4 * 4 + 1] = fmaf(x[p][ci], w.y, acc[p][c4 * 4 + 1]);
+                acc[p][c4 * 4 + 2] = fmaf(x[p][ci], w.z, acc[p][c4 * 4 + 2]);
+                acc[p][c4 * 4 + 3] = fmaf(x[p][ci], w.w, acc[p][c4 * 4 + 3]);
+              }
+            }
+          }
+        }
+    __syncthreads();
+  }
+
+  // ---- epilogue: + bias, PReLU, + residual, store
+  const long long ovox = (long long)a.od[0] * a.od[1] * a.od[2];
+#pragma unroll
+  for (int p = 0; p < PT; ++p) {
+    if (!ovalid[p]) continue;
+    const long long opos = ((long long)o0[p] * a.od[1] + o1) * a.od[2] + o2;
+    float imw = 1.f;
+    long long pl_off = 0;
+    bool pl_ok = true;
+    if (OUT_KIND == OUT_BLEND) {
+      const int g0 = a.wo[0] + o0[p];
+      pl_ok = g0 >= 0 && g0 < a.ad0;
+      pl_off = ((long long)g0 * a.ad1 + (a.wo[1] + o1)) * a.ad2 + (a.wo[2] + o2);
+      imw = fmaxf(__fmul_rn(__fmul_rn(a.imap0[o0[p]], a.imap1[o1]), a.imap2[o2]), a.imap_floor);
+    } else if (OUT_KIND == OUT_PLANAR) {
+      pl_off = (long long)n * a.pl_nstride + opos;
+    }
+#pragma unroll
+    for (int g = 0; g < CO_T / 8; ++g) {
+      const int cgo = coblk * (CO_T / 8) + g;
+      if (cgo >= a.cout_groups) continue;
+      float v[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float t = acc[p][g * 8 + c] + __ldg(a.bias + cgo * 8 + c);
+        if (a.act) t = prelu(t, a.alpha);
+        v[c] = t;
+      }
+      if (a.res) {
+        const float4* r = reinterpret_cast<const float4*>(
+            reinterpret_cast<const float*>(a.res) + (((long long)n * a.cout_groups + cgo) * ovox + opos) * 8);
+        const float4 r0 = __ldg(r), r1 = __ldg(r + 1);
+        v[0] += r0.x, v[1] += r0.y, v[2] += r0.z, v[3] += r0.w;
+        v[4] += r1.x, v[5] += r1.y, v[6] += r1.z, v[7] += r1.w;
+      }
+      if (OUT_KIND == OUT_CG8) {
+        float4* o = reinterpret_cast<float4*>(
+            reinterpret_cast<float*>(a.out) + (((long long)n * a.cout_groups + cgo) * ovox + opos) * 8);
+        o[0] = make_float4(v[0], v[1], v[2], v[3]);
+        o[1] = make_float4(v[4], v[5], v[6], v[7]);
+      } else if (pl_ok) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int ch = cgo * 8 + c;
+          if (ch < a.c_real) {
+            float* dst = a.pl_out + ch * a.pl_cstride + pl_off;
+            if (OUT_KIND == OUT_BLEND)
+              *dst = __fadd_rn(*dst, __fmul_rn(v[c], imw));  // seg *= w; out += seg (two roundings)
+            else
+              *dst = v[c];
+          }
+        }
+      }
+    }
+  }
+}
+
+// Per-axis tap of a stride-2 k3 p1 transposed conv: output parity class p, input shift sh -> kernel
+// index, or -1.  o = 2j + p reads in[j + sh] * W[k] with o + 1 - k = 2(j + sh).
+__device__ __forceinline__ int tconv_tap(int p, int sh) {
+  return p == 0 ? (sh == 0 ? 1 : -1) : (sh == 0 ? 2 : 0);
+}
+
+template <bool FLAT0>
+__global__ void __launch_bounds__(128) convT_fp32_kernel(const ConvArgs a) {
+  __shared__ __align__(16) float wsm[27 * 8 * CO_TT];
+  constexpr int NC0 = FLAT0 ? 1 : 2;
+  constexpr int NCLS = NC0 * 4;
+  const int tid = threadIdx.x;
+  const int t2 = tid & 7, t1 = (tid >> 3) & 3, t0 = tid >> 5;
+  const int nt2 = (a.id[2] + 7) >> 3, nt1 = (a.id[1] + 3) >> 2;
+  int tile = blockIdx.x;
+  const int b2 = tile % nt2;
+  tile /= nt2;
+  const int b1 = tile % nt1;
+  const int b0 = tile / nt1;
+  const int j2 = b2 * 8 + t2, j1 = b1 * 4 + t1, j0 = b0 * 4 + t0;
+  const bool jvalid = j0 < a.id[0] && j1 < a.id[1] && j2 < a.id[2];
+  const int n = blockIdx.z, coblk = blockIdx.y;
+  const int ntaps = a.k[0] * a.k[1] * a.k[2];
+  const int cgin = a.cg0 + a.cg1;
+  const long long ivox = (long long)a.id[0] * a.id[1] * a.id[2];
+
+  float acc[NCLS][CO_TT];
+#pragma unroll
+  for (int q = 0; q < NCLS; ++q)
+#pragma unroll
+    for (int c = 0; c < CO_TT; ++c) acc[q][c] = 0.f;
+
+  for (int cg = 0; cg < cgin; ++cg) {
+    const float4* wsrc =
+        reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.w) +
+                                        ((size_t)(coblk * cgin + cg) * ntaps * 8 * CO_TT));
+    for (int i = tid; i < ntaps * 8 * CO_TT / 4; i += 128) reinterpret_cast<float4*>(wsm)[i] = wsrc[i];
+    __syncthreads();
+    const float* src =
+        (cg < a.cg0) ? reinterpret_cast<const float*>(a.in0) + ((long long)n * a.cg0 + cg) * ivox * 8
+                     : reinterpret_cast<const float*>(a.in1) + ((long long)n * a.cg1 + (cg - a.cg0)) * ivox * 8;
+#pragma unroll
+    for (int sh0 = 0; sh0 < NC0; ++sh0)
+#pragma unroll
+      for (int sh1 = 0; sh1 < 2; ++sh1)
+#pragma unroll
+        for (int sh2 = 0; sh2 < 2; ++sh2) {
+          const int i0 = j0 + sh0, i1 = j1 + sh1, i2 = j2 + sh2;
+          const bool v = jvalid && i0 < a.id[0] && i1 < a.id[1] && i2 < a.id[2];
+          float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+          if (v) {
+            const float4* ptr =
+                reinterpret_cast<const float4*>(src + (((long long)i0 * a.id[1] + i1) * a.id[2] + i2) * 8);
+            lo = __ldg(ptr);
+            hi = __ldg(ptr + 1);
+          }
+          const float x[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+          for (int p0 = 0; p0 < NC0; ++p0)
+#pragma unroll
+            for (int p1 = 0; p1 < 2; ++p1)
+#pragma unroll
+              for (int p2 = 0; p2 < 2; ++p2) {
+                const int kk0 = FLAT0 ? 0 : tconv_tap(p0, sh0);
+                const int kk1 = tconv_tap(p1, sh1), kk2 = tconv_tap(p2, sh2);
+                if (kk0 < 0 || kk1 < 0 || kk2 < 0) continue;
+                const int tap = (kk0 * 3 + kk1) * 3 + kk2;
+                const int q = (p0 * 2 + p1) * 2 + p2;
+                const float* wt = wsm + tap * 8 * CO_TT;
+#pragma unroll
+                for (int ci = 0; ci < 8; ++ci) {
+                  const float4 w0 = *reinterpret_cast<const float4*>(wt + ci * CO_TT);
+                  const float4 w1 = *reinterpret_cast<const float4*>(wt + ci * CO_TT + 4);
+                  acc[q][0] = fmaf(x[ci], w0.x, acc[q][0]);
+                  acc[q][1] = fmaf(x[ci], w0.y, acc[q][1]);
+                  acc[q][2] = fmaf(x[ci], w0.z, acc[q][2]);
+                  acc[q][3] = fmaf(x[ci], w0.w, acc[q][3]);
+                  acc[q][4] = fmaf(x[ci], w1.x, acc[q][4]);
+                  acc[q][5] = fmaf(x[ci], w1.y, acc[q][5]);
+                  acc[q][6] = fmaf(x[ci], w1.z, acc[q][6]);
+                  acc[q][7] = fmaf(x[ci], w1.w, acc[q][7]);
+                }
+              }
+        }
+    __syncthreads();
+  }
+  if (!jvalid || coblk >= a.cout_groups) return;
+  const long long ovox = (long long)a.od[0] * a.od[1] * a.od[2];
+  float* obase = reinterpret_cast<float*>(a.out) + ((long long)n * a.cout_groups + coblk) * ovox * 8;
+#pragma unroll
+  for (int p0 = 0; p0 < NC0; ++p0)
+#pragma unroll
+    for (int p1 = 0; p1 < 2; ++p1)
+#pragma unroll
+      for (int p2 = 0; p2 < 2; ++p2) {
+        const int q = (p0 * 2 + p1) * 2 + p2;
+        const int oo0 = FLAT0 ? j0 : 2 * j0 + p0, oo1 = 2 * j1 + p1, oo2 = 2 * j2 + p2;
+        float v[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float t = acc[q][c] + __ldg(a.bias + coblk * 8 + c);
+          if (a.act) t = prelu(t, a.alpha);
+          v[c] = t;
+        }
+        float4* o = reinterpret_cast<float4*>(obase + (((long long)oo0 * a.od[1] + oo1) * a.od[2] + oo2) * 8);
+        o[0] = make_float4(v[0], v[1], v[2], v[3]);
+        o[1] = make_float4(v[4], v[5], v[6], v[7]);
+      }
+}
+
+}  // namespace
+
+int fp32_conv_cout_tile(bool transposed) { return transposed ? CO_TT : CO_T; }
+
+int launch_conv_fp32(const ConvArgs& a, bool in_planar, int out_kind, cudaStream_t st) {
+  const int nt = ceil_div(a.od[2], 8) * ceil_div(a.od[1], 4) * ceil_div(a.od[0], 4 * PT);
+  dim3 grid(nt, ceil_div(a.cout_groups * 8, CO_T), a.n);
+  if (in_planar) {
+    SGM_REQUIRE(out_kind == OUT_CG8, SGM_ERR_UNSUPPORTED, "planar-in conv writes CG8 only");
+    conv_fp32_kernel<true, OUT_CG8><<<grid, 128, 0, st>>>(a);
+  } else if (out_kind == OUT_CG8) {
+    conv_fp32_kernel<false, OUT_CG8><<<grid, 128, 0, st>>>(a);
+  } else if (out_kind == OUT_BLEND) {
+    conv_fp32_kernel<false, OUT_BLEND><<<grid, 128, 0, st>>>(a);
+  } else {
+    conv_fp32_kernel<false, OUT_PLANAR><<<grid, 128, 0, st>>>(a);
+  }
+  SGM_CUDA_CHECK(cudaGetLastError());
+  return SGM_OK;
+}
+
+int launch_convT_fp32(const ConvArgs& a, cudaStream_t st) {
+  const bool flat0 = a.k[0] == 1;
+  const int nt = ceil_div(a.id[2], 8) * ceil_div(a.id[1], 4) * ceil_div(a.id[0], 4);
+  dim3 grid(nt, a.cout_groups, a.n);
+  if (flat0)
+    convT_fp32_kernel<true><<<grid, 128, 0, st>>>(a);
+  else
+    convT_fp32_kernel<false><<<grid, 128, 0, st>>>(a);
+  SGM_CUDA_CHECK(cudaGetLastError());
+  return SGM_OK;
+}
+
+}  // namespace sgm

@@ -1,0 +1,505 @@
+// sgm_unet handle: weight packing, the per-window-batch layer program, and the C ABI for
+// Net.forward (seg/monai_unet.py:221-222) and the sliding-window inferer (seg/monai_unet.py:637-665).
+#include "common.cuh"
+
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+namespace sgm {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int launch_finalize(const float* acc, int channels, const sgm_sw_cfg* cfg, const int* starts_dev,
+                    const float* imap_dev[3], float* logits, uint8_t* labels, float* probs,
+                    cudaStream_t st);
+
+struct PackedConv {
+  int kind = SGM_KIND_IDENTITY;
+  int cin = 0, cout = 0, cgin = 0, cgout = 0;
+  int k[3] = {1, 1, 1}, s[3] = {1, 1, 1}, pad[3] = {0, 0, 0};
+  int act = 0;
+  float alpha = 0.f;
+  float* w32 = nullptr;   // fp32 family packing
+  float* bias = nullptr;  // [cgout*8] (padded to the cout tile)
+};
+
+}  // namespace sgm
+
+struct sgm_unet {
+  int spatial_dims = 3, cin = 1, cout = 1, n_levels = 0;
+  int channels[SGM_MAX_LEVELS] = {0}, strides[SGM_MAX_LEVELS] = {0};
+  int precision = SGM_PRECISION_FP32;
+  std::vector<sgm::PackedConv> convs;
+  int64_t last_launches = 0;
+};
+
+namespace sgm {
+
+namespace {
+
+// ---- fp32 packing: [coblk][cg][tap][ci 8][co CO_T], zero padded
+int pack_fp32(const sgm_conv_desc& d, PackedConv& pc, int spatial_dims) {
+  const bool tr = pc.kind == SGM_KIND_CONV_TRANSPOSE;
+  const int co_t = fp32_conv_cout_tile(tr);
+  const int ntaps = pc.k[0] * pc.k[1] * pc.k[2];
+  const int n_coblk = ceil_div(pc.cgout * 8, co_t);
+  const size_t nw = (size_t)n_coblk * pc.cgin * ntaps * 8 * co_t;
+  std::vector<float> w(nw, 0.f), b((size_t)n_coblk * co_t, 0.f);
+  // source taps: d.weight is [O][I][kk] (conv) or [I][O][kk] (convT) with kk = kernel^spatial_dims
+  const bool flip = tr && d.stride == 1;  // stride-1 transposed conv == conv with flipped kernel
+  for (int co = 0; co < pc.cout; ++co) {
+    b[co] = d.bias[co];
+    for (int ci = 0; ci < pc.cin; ++ci)
+      for (int t = 0; t < ntaps; ++t) {
+        const int st = flip ? (ntaps - 1 - t) : t;
+        const float v = tr ? d.weight[((size_t)ci * pc.cout + co) * ntaps + st]
+                           : d.weight[((size_t)co * pc.cin + ci) * ntaps + st];
+        const size_t dst = ((((size_t)(co / co_t) * pc.cgin + ci / 8) * ntaps + t) * 8 + ci % 8) * co_t + co % co_t;
+        w[dst] = v;
+      }
+  }
+  (void)spatial_dims;
+  if (cudaMalloc(&pc.w32, nw * sizeof(float)) != cudaSuccess ||
+      cudaMalloc(&pc.bias, b.size() * sizeof(float)) != cudaSuccess) {
+    set_error("cudaMalloc of packed weights failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return SGM_ERR_CUDA;
+  }
+  SGM_CUDA_CHECK(cudaMemcpy(pc.w32, w.data(), nw * sizeof(float), cudaMemcpyHostToDevice));
+  SGM_CUDA_CHECK(cudaMemcpy(pc.bias, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return SGM_OK;
+}
+
+struct Tensor {
+  void* p = nullptr;
+  int cg = 0;
+  int d[3] = {0, 0, 0};
+  long long vox() const { return (long long)d[0] * d[1] * d[2]; }
+};
+
+struct Bump {
+  char* base;
+  int64_t size, off = 0;
+  bool dry;
+  void* take(int64_t bytes) {
+    off = (off + 255) & ~int64_t(255);
+    void* p = dry ? nullptr : base + off;
+    off += bytes;
+    return p;
+  }
+};
+
+struct HeadTarget {
+  int kind;  // OUT_PLANAR or OUT_BLEND
+  float* out;
+  long long cstride, nstride;
+  int ad0, ad1, ad2;
+  const int* wo_host;  // [n][3] blend origins (host)
+  const float* imap[3];
+  float floor;
+};
+
+inline int out_dim(int i, int k, int s, int pad) { return (i + 2 * pad - k) / s + 1; }
+
+// Runs the whole network on `n` windows.  Input: planar volume + device window origins.
+int run_network(sgm_unet* net, const float* vol, long long vol_cstride, int vd1, int vd2,
+                const int* win_origin_dev, int n, const int roi[3], Bump& ws, const HeadTarget& head,
+                cudaStream_t st, bool dry) {
+  const int L = net->n_levels;
+  const size_t esz = net->precision == SGM_PRECISION_BF16 ? 2 : 4;
+  SGM_REQUIRE(net->precision == SGM_PRECISION_FP32, SGM_ERR_UNSUPPORTED,
+              "bf16 (tcgen05) network path is not wired into this build yet");
+  auto alloc = [&](int cg, const int d[3]) {
+    Tensor t;
+    t.cg = cg;
+    t.d[0] = d[0], t.d[1] = d[1], t.d[2] = d[2];
+    t.p = ws.take((int64_t)n * cg * t.vox() * 8 * esz);
+    return t;
+  };
+  auto base_args = [&](const PackedConv& pc, const Tensor& in0, const Tensor* in1, const int od[3]) {
+    ConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in0 = in0.p, a.cg0 = in0.cg;
+    a.in1 = in1 ? in1->p : nullptr, a.cg1 = in1 ? in1->cg : 0;
+    a.cin_real = pc.cin;
+    a.n = n;
+    for (int i = 0; i < 3; ++i) {
+      a.id[i] = in0.d[i], a.od[i] = od[i];
+      a.k[i] = pc.k[i], a.s[i] = pc.s[i], a.pad[i] = pc.pad[i];
+    }
+    a.w = pc.w32, a.bias = pc.bias, a.cout_groups = pc.cgout;
+    a.act = pc.act, a.alpha = pc.alpha;
+    a.c_real = pc.cout;
+    return a;
+  };
+  auto conv = [&](const PackedConv& pc, const Tensor& in0, const Tensor* in1, Tensor& out,
+                  const Tensor* res) -> int {
+    int od[3];
+    if (pc.kind == SGM_KIND_CONV_TRANSPOSE && pc.s[1] == 2) {
+      for (int i = 0; i < 3; ++i) od[i] = in0.d[i] * pc.s[i];
+    } else {
+      for (int i = 0; i < 3; ++i) od[i] = out_dim(in0.d[i], pc.k[i], pc.s[i], pc.pad[i]);
+    }
+    out = alloc(pc.cgout, od);
+    if (dry) return SGM_OK;
+    SGM_REQUIRE(in0.cg + (in1 ? in1->cg : 0) == pc.cgin, SGM_ERR_INVALID, "channel-group mismatch");
+    ConvArgs a = base_args(pc, in0, in1, od);
+    a.out = out.p;
+    a.res = res ? res->p : nullptr;
+    net->last_launches++;
+    if (pc.kind == SGM_KIND_CONV_TRANSPOSE && pc.s[1] == 2) return launch_convT_fp32(a, st);
+    return launch_conv_fp32(a, false, OUT_CG8, st);
+  };
+
+  // level dims
+  std::vector<PackedConv>& cv = net->convs;
+  Tensor cur;  // current CG8 activation (invalid for the planar network input)
+  std::vector<Tensor> skips(L);
+  int idx = 0;
+  for (int i = 0; i < L; ++i) {
+    const PackedConv& u0 = cv[idx], &u1 = cv[idx + 1], &rs = cv[idx + 2];
+    idx += 3;
+    Tensor t, r, x;
+    if (i == 0) {
+      // stem: reads windows straight from the planar volume
+      int od[3];
+      for (int a = 0; a < 3; ++a) od[a] = out_dim(roi[a], u0.k[a], u0.s[a], u0.pad[a]);
+      SGM_REQUIRE(rs.kind == SGM_KIND_CONV, SGM_ERR_UNSUPPORTED,
+                  "first down block with identity residual (stride 1 and num_channels == channels[0])");
+      t = alloc(u0.cgout, od);
+      r = alloc(rs.cgout, od);
+      if (!dry) {
+        for (int which = 0; which < 2; ++which) {
+          const PackedConv& pc = which ? rs : u0;
+          ConvArgs a;
+          memset(&a, 0, sizeof(a));
+          a.in0 = vol, a.cg0 = pc.cgin, a.cin_real = pc.cin, a.n = n;
+          for (int q = 0; q < 3; ++q) {
+            a.id[q] = roi[q], a.od[q] = od[q];
+            a.k[q] = pc.k[q], a.s[q] = pc.s[q], a.pad[q] = pc.pad[q];
+          }
+          a.w = pc.w32, a.bias = pc.bias, a.cout_groups = pc.cgout, a.act = pc.act, a.alpha = pc.alpha;
+          a.out = which ? r.p : t.p;
+          a.vol_cstride = vol_cstride, a.vd1 = vd1, a.vd2 = vd2, a.win_origin = win_origin_dev;
+          net->last_launches++;
+          int rc = launch_conv_fp32(a, true, OUT_CG8, st);
+          if (rc) return rc;
+        }
+      }
+    } else {
+      int rc = conv(u0, cur, nullptr, t, nullptr);
+      if (rc) return rc;
+      if (rs.kind == SGM_KIND_IDENTITY) {
+        r = cur;
+      } else {
+        rc = conv(rs, cur, nullptr, r, nullptr);
+        if (rc) return rc;
+      }
+    }
+    int rc = conv(u1, t, nullptr, x, &r);
+    if (rc) return rc;
+    skips[i] = x;
+    cur = x;
+  }
+  // bottom
+  Tensor sub;
+  {
+    const PackedConv& u0 = cv[idx], &u1 = cv[idx + 1], &rs = cv[idx + 2];
+    idx += 3;
+    Tensor t, r;
+    int rc = conv(u0, cur, nullptr, t, nullptr);
+    if (rc) return rc;
+    if (rs.kind == SGM_KIND_IDENTITY) {
+      r = cur;
+    } else {
+      rc = conv(rs, cur, nullptr, r, nullptr);
+      if (rc) return rc;
+    }
+    rc = conv(u1, t, nullptr, sub, &r);
+    if (rc) return rc;
+  }
+  // up path
+  for (int i = L - 1; i >= 0; --i) {
+    const PackedConv& ct = cv[idx], &ru = cv[idx + 1];
+    idx += 2;
+    Tensor u;
+    int rc = conv(ct, skips[i], &sub, u, nullptr);
+    if (rc) return rc;
+    if (i > 0) {
+      for (int a = 0; a < 3; ++a)
+        SGM_REQUIRE(u.d[a] == skips[i - 1].d[a], SGM_ERR_INVALID,
+                    "roi is not compatible with the strides (skip/up shape mismatch at level %d)", i);
+      Tensor o;
+      rc = conv(ru, u, nullptr, o, &u);
+      if (rc) return rc;
+      sub = o;
+    } else {
+      for (int a = 0; a < 3; ++a)
+        SGM_REQUIRE(u.d[a] == roi[a], SGM_ERR_INVALID,
+                    "roi %d along axis %d is not restored by the up path (must be divisible by the "
+                    "product of strides)", roi[a], a);
+      if (dry) break;
+      // head: conv C->C (conv only) + identity residual -> planar logits / blended accumulator
+      const long long uvox = u.vox();
+      ConvArgs a = base_args(ru, u, nullptr, u.d);
+      a.pl_out = head.out, a.pl_cstride = head.cstride, a.pl_nstride = head.nstride;
+      a.ad0 = head.ad0, a.ad1 = head.ad1, a.ad2 = head.ad2;
+      a.imap0 = head.imap[0], a.imap1 = head.imap[1], a.imap2 = head.imap[2];
+      a.imap_floor = head.floor;
+      if (head.kind == OUT_PLANAR) {
+        a.res = u.p;
+        net->last_launches++;
+        rc = launch_conv_fp32(a, false, OUT_PLANAR, st);
+        if (rc) return rc;
+      } else {
+        for (int w = 0; w < n; ++w) {  // one launch per window: plain RMW, MONAI's window order
+          ConvArgs b = a;
+          b.n = 1;
+          b.in0 = reinterpret_cast<const char*>(u.p) + (size_t)w * u.cg * uvox * 8 * esz;
+          b.res = b.in0;
+          b.wo[0] = head.wo_host[w * 3], b.wo[1] = head.wo_host[w * 3 + 1], b.wo[2] = head.wo_host[w * 3 + 2];
+          net->last_launches++;
+          rc = launch_conv_fp32(b, false, OUT_BLEND, st);
+          if (rc) return rc;
+        }
+      }
+    }
+  }
+  return SGM_OK;
+}
+
+int check_roi(const sgm_unet* net, const int32_t roi[3]) {
+  SGM_REQUIRE(roi && roi[0] > 0 && roi[1] > 0 && roi[2] > 0, SGM_ERR_INVALID, "bad roi");
+  SGM_REQUIRE(net->spatial_dims == 3 || roi[0] == 1, SGM_ERR_INVALID,
+              "2-D networks take roi = {1, h, w}");
+  return SGM_OK;
+}
+
+}  // namespace
+}  // namespace sgm
+
+using namespace sgm;
+
+extern "C" const char* sgm_last_error(void) { return g_err; }
+extern "C" int32_t sgm_version(void) { return 100; }
+
+extern "C" void sgm_unet_destroy(sgm_unet* net) {
+  if (!net) return;
+  for (auto& c : net->convs) {
+    if (c.w32) cudaFree(c.w32);
+    if (c.bias) cudaFree(c.bias);
+  }
+  delete net;
+}
+
+extern "C" int32_t sgm_unet_create(const sgm_unet_desc* d, sgm_unet** out) {
+  SGM_REQUIRE(d && out, SGM_ERR_INVALID, "sgm_unet_create: null argument");
+  *out = nullptr;
+  SGM_REQUIRE(d->spatial_dims == 2 || d->spatial_dims == 3, SGM_ERR_INVALID, "spatial_dims must be 2 or 3");
+  SGM_REQUIRE(d->n_levels >= 1 && d->n_levels < SGM_MAX_LEVELS, SGM_ERR_INVALID, "bad n_levels");
+  SGM_REQUIRE(d->n_convs == 3 * d->n_levels + 3 + 2 * d->n_levels, SGM_ERR_INVALID,
+              "expected %d convolutions in canonical order, got %d", 5 * d->n_levels + 3, d->n_convs);
+  SGM_REQUIRE(d->precision == SGM_PRECISION_FP32 || d->precision == SGM_PRECISION_BF16, SGM_ERR_INVALID,
+              "bad precision");
+  SGM_REQUIRE(d->in_channels >= 1 && d->in_channels <= 8, SGM_ERR_UNSUPPORTED,
+              "num_channels must be in 1..8, got %d", d->in_channels);
+  SGM_REQUIRE(d->out_channels >= 1 && d->out_channels <= 64, SGM_ERR_UNSUPPORTED,
+              "num_classes must be in 1..64, got %d", d->out_channels);
+  int dev_count = 0;
+  if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) {
+    set_error("no CUDA device: segmantic_b200 has no CPU fallback");
+    return SGM_ERR_CUDA;
+  }
+  for (int i = 0; i <= d->n_levels; ++i)
+    SGM_REQUIRE(d->channels[i] > 0 && d->channels[i] % 8 == 0, SGM_ERR_UNSUPPORTED,
+                "channels must be positive multiples of 8, got %d", d->channels[i]);
+  sgm_unet* net = new sgm_unet();
+  net->spatial_dims = d->spatial_dims, net->cin = d->in_channels, net->cout = d->out_channels;
+  net->n_levels = d->n_levels, net->precision = d->precision;
+  for (int i = 0; i <= d->n_levels; ++i) {
+    net->channels[i] = d->channels[i];
+    if (i < d->n_levels) net->strides[i] = d->strides[i];
+  }
+  net->convs.resize(d->n_convs);
+  for (int i = 0; i < d->n_convs; ++i) {
+    const sgm_conv_desc& c = d->convs[i];
+    PackedConv& pc = net->convs[i];
+    pc.kind = c.kind;
+    pc.cin = c.cin, pc.cout = c.cout;
+    pc.cgin = ceil_div(c.cin, 8), pc.cgout = ceil_div(c.cout, 8);
+    pc.act = c.has_act, pc.alpha = c.alpha;
+    if (c.kind == SGM_KIND_IDENTITY) continue;
+    if (!(c.kernel == 1 || c.kernel == 3) || !(c.stride == 1 || c.stride == 2) || !c.weight || !c.bias) {
+      set_error("conv %d: unsupported kernel/stride or null weights", i);
+      sgm_unet_destroy(net);
+      return SGM_ERR_UNSUPPORTED;
+    }
+    for (int a = 0; a < 3; ++a) {
+      const bool flat = d->spatial_dims == 2 && a == 0;
+      pc.k[a] = flat ? 1 : c.kernel;
+      pc.s[a] = flat ? 1 : c.stride;
+      pc.pad[a] = flat ? 0 : c.kernel / 2;
+    }
+    int rc = pack_fp32(c, pc, d->spatial_dims);
+    if (rc) {
+      sgm_unet_destroy(net);
+      return rc;
+    }
+  }
+  *out = net;
+  return SGM_OK;
+}
+
+extern "C" int64_t sgm_unet_last_launch_count(const sgm_unet* net) { return net ? net->last_launches : 0; }
+
+extern "C" int64_t sgm_unet_workspace_bytes(const sgm_unet* net, const int32_t roi[3], int32_t batch) {
+  if (!net || check_roi(net, roi) || batch < 1) return SGM_ERR_INVALID;
+  Bump ws{nullptr, 0, 0, true};
+  ws.take((int64_t)batch * 3 * sizeof(int));
+  HeadTarget head;
+  memset(&head, 0, sizeof(head));
+  int rc = run_network(const_cast<sgm_unet*>(net), nullptr, 0, 0, 0, nullptr, batch, roi, ws, head, 0, true);
+  if (rc) return rc;
+  return ws.off + 256;
+}
+
+extern "C" int32_t sgm_unet_forward(sgm_unet* net, const float* x_dev, float* logits_dev, int32_t batch,
+                                    const int32_t roi[3], void* workspace_dev, int64_t workspace_bytes,
+                                    void* stream) {
+  SGM_REQUIRE(net && x_dev && logits_dev && workspace_dev && batch >= 1, SGM_ERR_INVALID,
+              "sgm_unet_forward: bad argument");
+  int rc = check_roi(net, roi);
+  if (rc) return rc;
+  const int64_t need = sgm_unet_workspace_bytes(net, roi, batch);
+  if (need < 0) return (int32_t)need;
+  SGM_REQUIRE(workspace_bytes >= need, SGM_ERR_WORKSPACE, "workspace too small: need %lld bytes, got %lld",
+              (long long)need, (long long)workspace_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  Bump ws{(char*)workspace_dev, workspace_bytes, 0, false};
+  int* org_dev = (int*)ws.take((int64_t)batch * 3 * sizeof(int));
+  std::vector<int> org(batch * 3, 0);
+  for (int b = 0; b < batch; ++b) org[b * 3] = b * net->cin * roi[0];
+  SGM_CUDA_CHECK(cudaMemcpyAsync(org_dev, org.data(), org.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  const long long vox = (long long)roi[0] * roi[1] * roi[2];
+  HeadTarget head;
+  memset(&head, 0, sizeof(head));
+  head.kind = OUT_PLANAR, head.out = logits_dev, head.cstride = vox, head.nstride = vox * net->cout;
+  net->last_launches = 0;
+  return run_network(net, x_dev, vox, roi[1], roi[2], org_dev, batch, roi, ws, head, st, false);
+}
+
+static int check_cfg(const sgm_unet* net, const sgm_sw_cfg* cfg) {
+  SGM_REQUIRE(cfg, SGM_ERR_INVALID, "null sgm_sw_cfg");
+  for (int a = 0; a < 3; ++a) {
+    SGM_REQUIRE(cfg->roi[a] >= 1 && cfg->roi[a] <= 512 && cfg->dims[a] >= cfg->roi[a], SGM_ERR_INVALID,
+                "axis %d: roi %d / dims %d invalid (pad the volume to at least the roi)", a, cfg->roi[a],
+                cfg->dims[a]);
+    SGM_REQUIRE(cfg->n_starts[a] >= 1 && cfg->n_starts[a] <= SGM_MAX_STARTS, SGM_ERR_INVALID,
+                "axis %d: n_starts %d out of range", a, cfg->n_starts[a]);
+    for (int j = 0; j < cfg->n_starts[a]; ++j)
+      SGM_REQUIRE(cfg->starts[a][j] >= 0 && cfg->starts[a][j] + cfg->roi[a] <= cfg->dims[a], SGM_ERR_INVALID,
+                  "axis %d: window start %d outside the volume", a, cfg->starts[a][j]);
+    SGM_REQUIRE(cfg->imap[a], SGM_ERR_INVALID, "null importance table");
+  }
+  SGM_REQUIRE(cfg->acc_nx >= 1 && cfg->acc_x0 >= 0 && cfg->acc_x0 + cfg->acc_nx <= cfg->dims[0],
+              SGM_ERR_INVALID, "bad accumulator plane range");
+  if (net) return check_roi(net, cfg->roi);
+  return SGM_OK;
+}
+
+extern "C" int64_t sgm_sw_workspace_bytes(const sgm_unet* net, const sgm_sw_cfg* cfg) {
+  if (!net || check_cfg(net, cfg)) return SGM_ERR_INVALID;
+  const int64_t nwin = (int64_t)(cfg->a0_end - cfg->a0_begin) * cfg->n_starts[1] * cfg->n_starts[2];
+  const int B = std::max(1, std::min<int>(cfg->sw_batch, (int)std::max<int64_t>(nwin, 1)));
+  const int64_t net_bytes = sgm_unet_workspace_bytes(net, cfg->roi, B);
+  if (net_bytes < 0) return net_bytes;
+  return net_bytes + nwin * 3 * (int64_t)sizeof(int) + 3 * 512 * (int64_t)sizeof(float) + 1024;
+}
+
+extern "C" int32_t sgm_sw_accumulate(sgm_unet* net, const float* vol_dev, const sgm_sw_cfg* cfg,
+                                     float* acc_dev, void* workspace_dev, int64_t workspace_bytes,
+                                     void* stream) {
+  SGM_REQUIRE(net && vol_dev && acc_dev && workspace_dev, SGM_ERR_INVALID, "sgm_sw_accumulate: null argument");
+  int rc = check_cfg(net, cfg);
+  if (rc) return rc;
+  SGM_REQUIRE(cfg->a0_begin >= 0 && cfg->a0_end <= cfg->n_starts[0] && cfg->a0_begin <= cfg->a0_end,
+              SGM_ERR_INVALID, "bad axis-0 start range");
+  const int64_t need = sgm_sw_workspace_bytes(net, cfg);
+  SGM_REQUIRE(need >= 0 && workspace_bytes >= need, SGM_ERR_WORKSPACE,
+              "workspace too small: need %lld bytes, got %lld", (long long)need, (long long)workspace_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  // window list in MONAI order (axis 0 slowest)
+  std::vector<int> org_vol, org_acc;
+  for (int a0 = cfg->a0_begin; a0 < cfg->a0_end; ++a0) {
+    const int s0 = cfg->starts[0][a0];
+    SGM_REQUIRE(s0 >= cfg->vol_x0 && s0 + cfg->roi[0] <= cfg->vol_x0 + cfg->vol_nx, SGM_ERR_INVALID,
+                "window start %d needs planes outside vol_dev [%d,%d)", s0, cfg->vol_x0, cfg->vol_x0 + cfg->vol_nx);
+    for (int a1 = 0; a1 < cfg->n_starts[1]; ++a1)
+      for (int a2 = 0; a2 < cfg->n_starts[2]; ++a2) {
+        org_vol.push_back(s0 - cfg->vol_x0), org_vol.push_back(cfg->starts[1][a1]), org_vol.push_back(cfg->starts[2][a2]);
+        org_acc.push_back(s0 - cfg->acc_x0), org_acc.push_back(cfg->starts[1][a1]), org_acc.push_back(cfg->starts[2][a2]);
+      }
+  }
+  const int nwin = (int)(org_vol.size() / 3);
+  net->last_launches = 0;
+  if (nwin == 0) return SGM_OK;
+  Bump ws{(char*)workspace_dev, workspace_bytes, 0, false};
+  int* org_dev = (int*)ws.take((int64_t)nwin * 3 * sizeof(int));
+  float* imap_dev = (float*)ws.take(3 * 512 * sizeof(float));
+  SGM_CUDA_CHECK(cudaMemcpyAsync(org_dev, org_vol.data(), org_vol.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  for (int a = 0; a < 3; ++a)
+    SGM_CUDA_CHECK(cudaMemcpyAsync(imap_dev + a * 512, cfg->imap[a], cfg->roi[a] * sizeof(float),
+                                   cudaMemcpyHostToDevice, st));
+  const int B = std::max(1, std::min(cfg->sw_batch, nwin));
+  const long long plane = (long long)cfg->dims[1] * cfg->dims[2];
+  HeadTarget head;
+  memset(&head, 0, sizeof(head));
+  head.kind = OUT_BLEND, head.out = acc_dev;
+  head.cstride = (long long)cfg->acc_nx * plane;
+  head.ad0 = cfg->acc_nx, head.ad1 = cfg->dims[1], head.ad2 = cfg->dims[2];
+  for (int a = 0; a < 3; ++a) head.imap[a] = imap_dev + a * 512;
+  head.floor = cfg->imap_floor;
+  const int64_t ws_mark = ws.off;
+  for (int w0 = 0; w0 < nwin; w0 += B) {
+    const int nb = std::min(B, nwin - w0);
+    ws.off = ws_mark;
+    head.wo_host = org_acc.data() + (size_t)w0 * 3;
+    rc = run_network(net, vol_dev, (long long)cfg->vol_nx * plane, cfg->dims[1], cfg->dims[2],
+                     org_dev + (size_t)w0 * 3, nb, cfg->roi, ws, head, st, false);
+    if (rc) return rc;
+  }
+  return SGM_OK;
+}
+
+namespace {
+__constant__ int c_starts[3 * SGM_MAX_STARTS];
+__constant__ float c_imap[3 * 512];
+}  // namespace
+
+extern "C" int32_t sgm_sw_finalize(const float* acc_dev, int32_t channels, const sgm_sw_cfg* cfg,
+                                   float* logits_dev, uint8_t* labels_dev, float* probs_dev, void* stream) {
+  SGM_REQUIRE(acc_dev && channels >= 1, SGM_ERR_INVALID, "sgm_sw_finalize: bad argument");
+  int rc = check_cfg(nullptr, cfg);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  SGM_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_starts, cfg->starts, sizeof(int) * 3 * SGM_MAX_STARTS, 0,
+                                         cudaMemcpyHostToDevice, st));
+  for (int a = 0; a < 3; ++a)
+    SGM_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_imap, cfg->imap[a], sizeof(float) * cfg->roi[a],
+                                           sizeof(float) * 512 * a, cudaMemcpyHostToDevice, st));
+  int* starts_ptr = nullptr;
+  float* imap_ptr = nullptr;
+  SGM_CUDA_CHECK(cudaGetSymbolAddress((void**)&starts_ptr, c_starts));
+  SGM_CUDA_CHECK(cudaGetSymbolAddress((void**)&imap_ptr, c_imap));
+  const float* imaps[3] = {imap_ptr, imap_ptr + 512, imap_ptr + 1024};
+  return launch_finalize(acc_dev, channels, cfg, starts_ptr, imaps, logits_dev, labels_dev, probs_dev, st);
+}

@@ -1,0 +1,254 @@
+"""Device engine: the MONAI-UNet + sliding-window operators, executed by the sm_100a library.
+
+``UNetB200`` stands where ``Net._model`` (``monai.networks.nets.UNet``, eval mode) stands in the
+reference (``/root/reference/src/segmantic/seg/monai_unet.py:114-124,221-222``) and
+``sliding_window_inference`` where ``SlidingWindowInferer(...)(image, net)`` does (``:637-639,665``).
+PyTorch supplies device buffers and the stream only; all arithmetic is in ``libsegmantic_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+
+from .. import _lib
+from .sliding_window import Schedule, make_schedule
+from .unet_spec import (KIND_IDENTITY, fold_batchnorm, unet_conv_specs)
+
+
+def _require_cuda(device) -> torch.device:
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("segmantic_b200 runs on CUDA devices only (no CPU fallback); "
+                           f"got device {device}")
+    if not torch.cuda.is_available():
+        raise RuntimeError("no CUDA device available: segmantic_b200 has no CPU fallback")
+    return device
+
+
+def _stream_ptr(device) -> int:
+    return int(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _precision_code(precision: str) -> int:
+    p = str(precision).lower()
+    if p in ("fp32", "float32", "32"):
+        return _lib.PRECISION_FP32
+    if p in ("bf16", "bfloat16"):
+        return _lib.PRECISION_BF16
+    raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
+
+
+class UNetB200:
+    """Frozen, eval-mode MONAI UNet (num_res_units=2, BATCH norm folded, PReLU) on one B200."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], *, spatial_dims: int = 3, in_channels: int = 1,
+                 out_channels: int, channels=(16, 32, 64, 128, 256), strides=(2, 2, 2, 2),
+                 device="cuda:0", precision: str = "fp32"):
+        self.device = _require_cuda(device)
+        self.spatial_dims, self.in_channels, self.out_channels = int(spatial_dims), int(in_channels), int(out_channels)
+        self.channels, self.strides = tuple(int(c) for c in channels), tuple(int(s) for s in strides)
+        self.precision = str(precision).lower()
+        self._lib = _lib.load()
+        specs = unet_conv_specs(self.in_channels, self.out_channels, self.channels, self.strides)
+        folded = fold_batchnorm(state_dict, specs)
+        n = len(self.channels) - 1
+        convs = (_lib.ConvDesc * len(folded))()
+        keep = []  # keep host tensors alive until create returns
+        for i, f in enumerate(folded):
+            d = convs[i]
+            d.kind, d.cin, d.cout = f.spec.kind, f.spec.cin, f.spec.cout
+            d.kernel, d.stride = f.spec.kernel, f.spec.stride
+            d.has_act, d.alpha = int(f.spec.has_adn), float(f.alpha)
+            if f.spec.kind != KIND_IDENTITY:
+                w = f.weight.contiguous().cpu()
+                b = f.bias.contiguous().cpu()
+                keep += [w, b]
+                d.weight = C.cast(w.data_ptr(), C.POINTER(C.c_float))
+                d.bias = C.cast(b.data_ptr(), C.POINTER(C.c_float))
+        desc = _lib.UnetDesc()
+        desc.spatial_dims, desc.in_channels, desc.out_channels = self.spatial_dims, self.in_channels, self.out_channels
+        desc.n_levels = n
+        for i, c in enumerate(self.channels):
+            desc.channels[i] = c
+        for i, s in enumerate(self.strides[:n]):
+            desc.strides[i] = s
+        desc.precision = _precision_code(precision)
+        desc.n_convs, desc.convs = len(folded), convs
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.sgm_unet_create(C.byref(desc), C.byref(handle)), "sgm_unet_create")
+        self._handle = handle
+        self._ws: Optional[torch.Tensor] = None
+        del keep
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h:
+            try:
+                self._lib.sgm_unet_destroy(h)
+            except Exception:
+                pass
+            self._handle = None
+
+    # -- helpers
+    def roi3(self, roi: Sequence[int]) -> Tuple[int, int, int]:
+        roi = tuple(int(r) for r in roi)
+        if self.spatial_dims == 2:
+            roi = roi[-2:]
+            return (1,) + roi
+        if len(roi) != 3:
+            raise ValueError(f"roi must have 3 entries for a 3-D network, got {roi}")
+        return roi
+
+    def _workspace(self, nbytes: int) -> torch.Tensor:
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    @property
+    def last_launch_count(self) -> int:
+        return int(self._lib.sgm_unet_last_launch_count(self._handle))
+
+    # -- Net.forward
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """``[B, Cin, *roi]`` float32 CUDA tensor -> ``[B, C, *roi]`` float32 logits."""
+        if x.device != self.device or x.dtype != torch.float32:
+            raise ValueError("input must be a float32 tensor on the network's CUDA device")
+        if x.dim() != self.spatial_dims + 2 or x.shape[1] != self.in_channels:
+            raise ValueError(f"expected [B, {self.in_channels}, *spatial({self.spatial_dims})], got {tuple(x.shape)}")
+        x = x.contiguous()
+        B = x.shape[0]
+        roi = self.roi3(x.shape[2:])
+        out = torch.empty((B, self.out_channels) + tuple(x.shape[2:]), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            need = self._lib.sgm_unet_workspace_bytes(self._handle, _lib.i3(roi), B)
+            _lib.check(need, "sgm_unet_workspace_bytes")
+            ws = self._workspace(need)
+            _lib.check(self._lib.sgm_unet_forward(self._handle, x.data_ptr(), out.data_ptr(), B, _lib.i3(roi),
+                                                  ws.data_ptr(), ws.numel(), _stream_ptr(self.device)),
+                       "sgm_unet_forward")
+        return out
+
+    __call__ = forward
+
+
+def _make_cfg(sched: Schedule, sw_batch: int, a0=None, vol=None, acc=None):
+    cfg = _lib.SwCfg()
+    keep = []
+    for a in range(3):
+        cfg.dims[a] = sched.padded_size[a]
+        cfg.roi[a] = sched.roi[a]
+        n = len(sched.starts[a])
+        if n > _lib.SGM_MAX_STARTS:
+            raise ValueError(f"too many window starts along axis {a}: {n} > {_lib.SGM_MAX_STARTS}")
+        cfg.n_starts[a] = n
+        for j, s in enumerate(sched.starts[a]):
+            cfg.starts[a][j] = s
+        t = sched.tables[a].contiguous().to(torch.float32).cpu()
+        keep.append(t)
+        cfg.imap[a] = C.cast(t.data_ptr(), C.POINTER(C.c_float))
+    cfg.imap_floor = float(sched.floor)
+    cfg.sw_batch = int(sw_batch)
+    cfg.a0_begin, cfg.a0_end = a0 if a0 is not None else (0, len(sched.starts[0]))
+    cfg.vol_x0, cfg.vol_nx = vol if vol is not None else (0, sched.padded_size[0])
+    cfg.acc_x0, cfg.acc_nx = acc if acc is not None else (0, sched.padded_size[0])
+    return cfg, keep
+
+
+def sliding_window_inference(inputs: torch.Tensor, roi_size: Sequence[int], sw_batch_size: int,
+                             predictor: UNetB200, overlap: float = 0.25, mode: str = "constant",
+                             sigma_scale: float = 0.125, *, return_labels: bool = False,
+                             return_probs: bool = False, return_logits: bool = True, slab: Optional[dict] = None):
+    """MONAI ``sliding_window_inference`` semantics on the device.
+
+    ``inputs`` is ``[1, Cin, *spatial]`` float32 on the predictor's device.  Returns the blended
+    logits ``[1, C, *spatial]`` (and/or ``labels`` uint8 ``[1, 1, *spatial]`` = argmax, ties -> lowest
+    class; ``probs`` = softmax of the blended logits) as a dict when more than the logits are asked for.
+    With ``slab`` (from ``sliding_window.slab_partition``) only the rank's planes are computed and
+    returned (axis 0 of the result covers ``[slab.x0, slab.x1)``).
+    """
+    net = predictor
+    if inputs.dim() != net.spatial_dims + 2 or inputs.shape[0] != 1:
+        raise ValueError(f"inputs must be [1, Cin, *spatial], got {tuple(inputs.shape)}")
+    if inputs.device != net.device or inputs.dtype != torch.float32:
+        raise ValueError("inputs must be float32 on the predictor's CUDA device")
+    spatial = tuple(inputs.shape[2:])
+    size3 = (1,) + spatial if net.spatial_dims == 2 else spatial
+    roi3 = net.roi3(roi_size)
+    sched = make_schedule(size3, roi3, overlap, mode, sigma_scale)
+    vol = inputs[0].reshape((net.in_channels,) + size3)
+    if sched.padded_size != size3:  # symmetric zero padding up to the roi (cropped again below)
+        pad = []
+        for a in (2, 1, 0):
+            lo = sched.pad_lo[a]
+            pad += [lo, sched.padded_size[a] - size3[a] - lo]
+        vol = torch.nn.functional.pad(vol, pad, mode="constant", value=0.0)
+    vol = vol.contiguous()
+    lib = net._lib
+    C_out = net.out_channels
+    if slab is None:
+        x0, x1 = 0, sched.padded_size[0]
+        a0 = (0, len(sched.starts[0]))
+        vol_rng = (0, sched.padded_size[0])
+    else:
+        x0, x1 = int(slab["x0"]), int(slab["x1"])
+        a0 = (int(slab["a0_begin"]), int(slab["a0_end"]))
+        vol_rng = (int(slab["vol_x0"]), int(slab["vol_x1"]) - int(slab["vol_x0"]))
+        vol = vol[:, slab["vol_x0"]:slab["vol_x1"]].contiguous()
+    nx = x1 - x0
+    plane = (sched.padded_size[1], sched.padded_size[2])
+    out: dict = {}
+    if nx <= 0:
+        empty = (0,) + plane
+        if return_logits:
+            out["logits"] = torch.empty((1, C_out) + empty, device=net.device)
+        if return_labels:
+            out["labels"] = torch.empty((1, 1) + empty, dtype=torch.uint8, device=net.device)
+        if return_probs:
+            out["probs"] = torch.empty((1, C_out) + empty, device=net.device)
+        return out if (return_labels or return_probs) else out["logits"]
+    cfg, keep = _make_cfg(sched, sw_batch_size, a0, vol_rng, (x0, nx))
+    acc = torch.zeros((C_out, nx) + plane, dtype=torch.float32, device=net.device)
+    with torch.cuda.device(net.device):
+        st = _stream_ptr(net.device)
+        need = lib.sgm_sw_workspace_bytes(net._handle, C.byref(cfg))
+        _lib.check(need, "sgm_sw_workspace_bytes")
+        ws = net._workspace(need)
+        _lib.check(lib.sgm_sw_accumulate(net._handle, vol.data_ptr(), C.byref(cfg), acc.data_ptr(),
+                                         ws.data_ptr(), ws.numel(), st), "sgm_sw_accumulate")
+        logits = torch.empty_like(acc) if return_logits else None
+        labels = torch.empty((nx,) + plane, dtype=torch.uint8, device=net.device) if return_labels else None
+        probs = torch.empty_like(acc) if return_probs else None
+        _lib.check(lib.sgm_sw_finalize(acc.data_ptr(), C_out, C.byref(cfg),
+                                       logits.data_ptr() if logits is not None else None,
+                                       labels.data_ptr() if labels is not None else None,
+                                       probs.data_ptr() if probs is not None else None, st),
+                   "sgm_sw_finalize")
+    del keep
+
+    def crop(t, lead):
+        # undo the roi padding (axes 1, 2 always; axis 0 only without a slab)
+        sl = [slice(None)] * lead
+        for a in range(3):
+            lo = sched.pad_lo[a]
+            if a == 0 and slab is not None:
+                sl.append(slice(None))
+            else:
+                sl.append(slice(lo, lo + size3[a]))
+        t = t[tuple(sl)]
+        if net.spatial_dims == 2:
+            t = t.squeeze(lead)
+        return t.unsqueeze(0)
+
+    if logits is not None:
+        out["logits"] = crop(logits, 1)
+    if labels is not None:
+        out["labels"] = crop(labels.unsqueeze(0), 1)
+    if probs is not None:
+        out["probs"] = crop(probs, 1)
+    if return_labels or return_probs:
+        return out
+    return out["logits"]

@@ -1,0 +1,129 @@
+"""Host-side schedule of the sliding-window inferer (no device work here).
+
+Mirrors what ``SlidingWindowInferer(roi_size=net.spatial_size, sw_batch_size=4, device=device)``
+(``/root/reference/src/segmantic/seg/monai_unet.py:637-639``) computes before it calls the network:
+symmetric zero padding up to the ROI, the scan interval, the per-axis window starts (last window
+shifted back inside) and the importance map (constant, or MONAI >= 1.2's separable Gaussian with its
+1e-3 floor).  Defaults are the reference's: overlap 0.25, mode "constant", sigma_scale 0.125.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import List, Sequence, Tuple
+
+import torch
+
+
+def scan_interval(image_size: Sequence[int], roi_size: Sequence[int], overlap: float) -> Tuple[int, ...]:
+    if not 0.0 <= overlap < 1.0:
+        raise ValueError(f"overlap must be >= 0 and < 1, got {overlap}.")
+    out = []
+    for size, roi in zip(image_size, roi_size):
+        out.append(int(roi) if roi == size else max(int(roi * (1 - overlap)), 1))
+    return tuple(out)
+
+
+def axis_starts(size: int, roi: int, interval: int) -> List[int]:
+    num = int(math.ceil(float(size) / interval))
+    for d in range(num):
+        if d * interval + roi >= size:
+            num = d + 1
+            break
+    starts = []
+    for i in range(num):
+        s = i * interval
+        starts.append(s - max(s + roi - size, 0))
+    return starts
+
+
+def importance_tables(roi: Sequence[int], mode: str = "constant", sigma_scale: float = 0.125):
+    """Per-axis 1-D tables and the floor; window weight = max((t0[i]*t1[j])*t2[k], floor)."""
+    mode = str(mode).lower()
+    if mode == "constant":
+        return [torch.ones(int(r), dtype=torch.float32) for r in roi], 0.0
+    if mode != "gaussian":
+        raise ValueError(f"mode must be 'constant' or 'gaussian', got {mode!r}")
+    tables = []
+    for n in roi:
+        n = int(n)
+        sigma = sigma_scale * n
+        x = torch.arange(start=-(n - 1) / 2.0, end=(n - 1) / 2.0 + 1, dtype=torch.float32)
+        tables.append(torch.exp(x ** 2 / (-2 * sigma ** 2)))
+    # floor = max(min of the separable product, 1e-3); the minimum sits at a corner
+    prod = None
+    for t in tables:
+        m = torch.minimum(t[0], t[-1])
+        prod = m if prod is None else prod * m
+    # the product of per-axis minima equals the map's minimum only if multiplication order matches
+    # MONAI's ((t0*t1)*t2) -- it does, all factors are the corner values.
+    floor = max(float(prod), 1e-3)
+    return tables, floor
+
+
+@dataclass
+class Schedule:
+    image_size: Tuple[int, ...]      # original spatial size (3 axes; axis 0 == 1 for 2-D)
+    padded_size: Tuple[int, ...]     # max(image, roi)
+    pad_lo: Tuple[int, ...]
+    roi: Tuple[int, ...]
+    starts: List[List[int]]          # per axis
+    tables: List[torch.Tensor] = field(repr=False, default_factory=list)
+    floor: float = 0.0
+
+    @property
+    def n_windows(self) -> int:
+        return len(self.starts[0]) * len(self.starts[1]) * len(self.starts[2])
+
+    def windows(self):
+        """All window starts in MONAI order (axis 0 slowest)."""
+        return [(a, b, c) for a in self.starts[0] for b in self.starts[1] for c in self.starts[2]]
+
+
+def make_schedule(image_size: Sequence[int], roi_size: Sequence[int], overlap: float = 0.25,
+                  mode: str = "constant", sigma_scale: float = 0.125) -> Schedule:
+    image_size = tuple(int(s) for s in image_size)
+    roi = tuple(int(r) for r in roi_size)
+    if len(image_size) != 3 or len(roi) != 3:
+        raise ValueError("schedule works on 3 axes (use a leading axis of size 1 for 2-D)")
+    padded = tuple(max(s, r) for s, r in zip(image_size, roi))
+    pad_lo = tuple((p - s) // 2 for p, s in zip(padded, image_size))
+    interval = scan_interval(padded, roi, overlap)
+    starts = [axis_starts(padded[a], roi[a], interval[a]) for a in range(3)]
+    tables, floor = importance_tables(roi, mode, sigma_scale)
+    return Schedule(image_size, padded, pad_lo, roi, starts, tables, floor)
+
+
+def slab_partition(schedule: Schedule, world_size: int) -> List[dict]:
+    """Partition axis 0 into `world_size` output slabs with ROI halos (multi-GPU driver).
+
+    Rank r owns output planes [x0, x1) and must run every window row (axis-0 start index) that
+    intersects them, in order, which makes its planes bit-identical to the single-GPU result.  Cuts are
+    placed at window starts so that window rows are balanced across ranks.  Returns per rank:
+    ``dict(x0, x1, a0_begin, a0_end, vol_x0, vol_x1)``.
+    """
+    s0 = schedule.starts[0]
+    n0, roi0, size0 = len(s0), schedule.roi[0], schedule.padded_size[0]
+    world_size = max(1, int(world_size))
+    # balance the number of window rows each rank executes: choose cuts among candidate planes
+    cuts = [0]
+    for r in range(1, world_size):
+        # plane where rank r begins: the start of the window row at the r/world quantile
+        j = min(n0 - 1, max(1, round(r * n0 / world_size)))
+        cut = s0[j] if j < n0 else size0
+        # a cut inside the overlap of rows j-1 and j: put it mid-overlap to share the halo evenly
+        cut = min(size0, max(cuts[-1], (s0[j] + min(size0, s0[j - 1] + roi0)) // 2))
+        cuts.append(cut)
+    cuts.append(size0)
+    parts = []
+    for r in range(world_size):
+        x0, x1 = cuts[r], cuts[r + 1]
+        rows = [j for j in range(n0) if s0[j] < x1 and s0[j] + roi0 > x0] if x1 > x0 else []
+        if rows:
+            a0b, a0e = rows[0], rows[-1] + 1
+            vx0, vx1 = s0[a0b], s0[a0e - 1] + roi0
+        else:
+            a0b = a0e = 0
+            vx0 = vx1 = x0
+        parts.append(dict(x0=x0, x1=x1, a0_begin=a0b, a0_end=a0e, vol_x0=vx0, vol_x1=vx1))
+    return parts
