@@ -73,8 +73,8 @@ enum { OUT_CG8 = 0, OUT_BLEND = 1, OUT_PLANAR = 2 };
 
 // ---- fp32 CUDA-core family (conv_fp32.cu)
 int fp32_conv_cout_tile(bool transposed);
-int launch_conv_fp32(const ConvArgs& a, bool in_planar, int out_kind, cudaStream_t st);
-int launch_convT_fp32(const ConvArgs& a, cudaStream_t st);
+int launch_conv_fp32(const ConvArgs& a, bool bf16_storage, bool in_planar, int out_kind, cudaStream_t st);
+int launch_convT_fp32(const ConvArgs& a, bool bf16_storage, cudaStream_t st);
 
 // ---- bf16 tcgen05 family (conv_tc.cu)
 struct TcConvPlan;

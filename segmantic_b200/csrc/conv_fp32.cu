@@ -1,6 +1,9 @@
-// fp32 CUDA-core convolution family: the `precision="fp32"` path (reference default numerics:
-// the reference runs fp32 always, seg/monai_unet.py:551-670) and the on-device cross-check for the
-// tcgen05 bf16 family.  Direct (gather-form) convolution over CG8 activations, FFMA accumulate.
+// CUDA-core convolution family (FFMA, fp32 accumulate), templated on the CG8 storage type:
+//   float          the `precision="fp32"` path (reference numerics: the reference runs fp32 always,
+//                  seg/monai_unet.py:551-670);
+//   __nv_bfloat16  the on-device cross-check of the tcgen05 family (same storage, same rounding
+//                  points) and the executor for layer shapes the tcgen05 family does not cover.
+// Direct (gather-form) convolution over CG8 activations.
 //
 //   conv_fp32_kernel   k in {1,3}^3, stride in {1,2}^3, zero padding k/2 at the WINDOW border
 //                      (each ROI window is convolved in isolation, as MONAI does).
@@ -22,7 +25,36 @@ constexpr int PT = 2;      // output positions per thread (along d0), conv
 
 __device__ __forceinline__ float prelu(float v, float alpha) { return v > 0.f ? v : alpha * v; }
 
-template <bool IN_PLANAR, int OUT_KIND>
+// One CG8 voxel-group (8 channels): 32 B in fp32 storage, 16 B in bf16 storage.
+__device__ __forceinline__ void load8(const float* p, float x[8]) {
+  const float4 lo = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 hi = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  x[0] = lo.x, x[1] = lo.y, x[2] = lo.z, x[3] = lo.w, x[4] = hi.x, x[5] = hi.y, x[6] = hi.z, x[7] = hi.w;
+}
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float x[8]) {
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    x[2 * i] = __uint_as_float(w[i] << 16);
+    x[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ void store8(float* p, const float v[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float v[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 b = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    w[i] = *reinterpret_cast<const uint32_t*>(&b);
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+template <typename T, bool IN_PLANAR, int OUT_KIND>
 __global__ void __launch_bounds__(128) conv_fp32_kernel(const ConvArgs a) {
   __shared__ __align__(16) float wsm[27 * 8 * CO_T];
   const int tid = threadIdx.x;
@@ -65,11 +97,11 @@ __global__ void __launch_bounds__(128) conv_fp32_kernel(const ConvArgs a) {
                                         ((size_t)(coblk * cgin + cg) * ntaps * 8 * CO_T));
     for (int i = tid; i < ntaps * 8 * CO_T / 4; i += 128) reinterpret_cast<float4*>(wsm)[i] = wsrc[i];
     __syncthreads();
-    const float* src = nullptr;
+    const T* src = nullptr;
     if (!IN_PLANAR) {
       src = (cg < a.cg0)
-                ? reinterpret_cast<const float*>(a.in0) + ((long long)n * a.cg0 + cg) * ivox * 8
-                : reinterpret_cast<const float*>(a.in1) + ((long long)n * a.cg1 + (cg - a.cg0)) * ivox * 8;
+                ? reinterpret_cast<const T*>(a.in0) + ((long long)n * a.cg0 + cg) * ivox * 8
+                : reinterpret_cast<const T*>(a.in1) + ((long long)n * a.cg1 + (cg - a.cg0)) * ivox * 8;
     }
     int tap = 0;
     for (int k0 = 0; k0 < a.k[0]; ++k0)
@@ -96,15 +128,9 @@ __global__ void __launch_bounds__(128) conv_fp32_kernel(const ConvArgs a) {
                 }
               }
             } else {
-              float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
-              if (v) {
-                const float4* ptr = reinterpret_cast<const float4*>(
-                    src + (((long long)i0 * a.id[1] + i1) * a.id[2] + i2) * 8);
-                lo = __ldg(ptr);
-                hi = __ldg(ptr + 1);
-              }
-              x[p][0] = lo.x, x[p][1] = lo.y, x[p][2] = lo.z, x[p][3] = lo.w;
-              x[p][4] = hi.x, x[p][5] = hi.y, x[p][6] = hi.z, x[p][7] = hi.w;
+#pragma unroll
+              for (int ci = 0; ci < 8; ++ci) x[p][ci] = 0.f;
+              if (v) load8(src + (((long long)i0 * a.id[1] + i1) * a.id[2] + i2) * 8, x[p]);
             }
           }
           const float* wt = wsm + tap * 8 * CO_T;
@@ -155,17 +181,13 @@ __global__ void __launch_bounds__(128) conv_fp32_kernel(const ConvArgs a) {
         v[c] = t;
       }
       if (a.res) {
-        const float4* r = reinterpret_cast<const float4*>(
-            reinterpret_cast<const float*>(a.res) + (((long long)n * a.cout_groups + cgo) * ovox + opos) * 8);
-        const float4 r0 = __ldg(r), r1 = __ldg(r + 1);
-        v[0] += r0.x, v[1] += r0.y, v[2] += r0.z, v[3] += r0.w;
-        v[4] += r1.x, v[5] += r1.y, v[6] += r1.z, v[7] += r1.w;
+        float r[8];
+        load8(reinterpret_cast<const T*>(a.res) + (((long long)n * a.cout_groups + cgo) * ovox + opos) * 8, r);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] += r[c];
       }
       if (OUT_KIND == OUT_CG8) {
-        float4* o = reinterpret_cast<float4*>(
-            reinterpret_cast<float*>(a.out) + (((long long)n * a.cout_groups + cgo) * ovox + opos) * 8);
-        o[0] = make_float4(v[0], v[1], v[2], v[3]);
-        o[1] = make_float4(v[4], v[5], v[6], v[7]);
+        store8(reinterpret_cast<T*>(a.out) + (((long long)n * a.cout_groups + cgo) * ovox + opos) * 8, v);
       } else if (pl_ok) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -189,7 +211,7 @@ __device__ __forceinline__ int tconv_tap(int p, int sh) {
   return p == 0 ? (sh == 0 ? 1 : -1) : (sh == 0 ? 2 : 0);
 }
 
-template <bool FLAT0>
+template <typename T, bool FLAT0>
 __global__ void __launch_bounds__(128) convT_fp32_kernel(const ConvArgs a) {
   __shared__ __align__(16) float wsm[27 * 8 * CO_TT];
   constexpr int NC0 = FLAT0 ? 1 : 2;
@@ -221,9 +243,9 @@ __global__ void __launch_bounds__(128) convT_fp32_kernel(const ConvArgs a) {
                                         ((size_t)(coblk * cgin + cg) * ntaps * 8 * CO_TT));
     for (int i = tid; i < ntaps * 8 * CO_TT / 4; i += 128) reinterpret_cast<float4*>(wsm)[i] = wsrc[i];
     __syncthreads();
-    const float* src =
-        (cg < a.cg0) ? reinterpret_cast<const float*>(a.in0) + ((long long)n * a.cg0 + cg) * ivox * 8
-                     : reinterpret_cast<const float*>(a.in1) + ((long long)n * a.cg1 + (cg - a.cg0)) * ivox * 8;
+    const T* src =
+        (cg < a.cg0) ? reinterpret_cast<const T*>(a.in0) + ((long long)n * a.cg0 + cg) * ivox * 8
+                     : reinterpret_cast<const T*>(a.in1) + ((long long)n * a.cg1 + (cg - a.cg0)) * ivox * 8;
 #pragma unroll
     for (int sh0 = 0; sh0 < NC0; ++sh0)
 #pragma unroll
@@ -232,14 +254,8 @@ __global__ void __launch_bounds__(128) convT_fp32_kernel(const ConvArgs a) {
         for (int sh2 = 0; sh2 < 2; ++sh2) {
           const int i0 = j0 + sh0, i1 = j1 + sh1, i2 = j2 + sh2;
           const bool v = jvalid && i0 < a.id[0] && i1 < a.id[1] && i2 < a.id[2];
-          float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
-          if (v) {
-            const float4* ptr =
-                reinterpret_cast<const float4*>(src + (((long long)i0 * a.id[1] + i1) * a.id[2] + i2) * 8);
-            lo = __ldg(ptr);
-            hi = __ldg(ptr + 1);
-          }
-          const float x[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+          float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (v) load8(src + (((long long)i0 * a.id[1] + i1) * a.id[2] + i2) * 8, x);
 #pragma unroll
           for (int p0 = 0; p0 < NC0; ++p0)
 #pragma unroll
@@ -271,7 +287,7 @@ __global__ void __launch_bounds__(128) convT_fp32_kernel(const ConvArgs a) {
   }
   if (!jvalid || coblk >= a.cout_groups) return;
   const long long ovox = (long long)a.od[0] * a.od[1] * a.od[2];
-  float* obase = reinterpret_cast<float*>(a.out) + ((long long)n * a.cout_groups + coblk) * ovox * 8;
+  T* obase = reinterpret_cast<T*>(a.out) + ((long long)n * a.cout_groups + coblk) * ovox * 8;
 #pragma unroll
   for (int p0 = 0; p0 < NC0; ++p0)
 #pragma unroll
@@ -287,9 +303,7 @@ __global__ void __launch_bounds__(128) convT_fp32_kernel(const ConvArgs a) {
           if (a.act) t = prelu(t, a.alpha);
           v[c] = t;
         }
-        float4* o = reinterpret_cast<float4*>(obase + (((long long)oo0 * a.od[1] + oo1) * a.od[2] + oo2) * 8);
-        o[0] = make_float4(v[0], v[1], v[2], v[3]);
-        o[1] = make_float4(v[4], v[5], v[6], v[7]);
+        store8(obase + (((long long)oo0 * a.od[1] + oo1) * a.od[2] + oo2) * 8, v);
       }
 }
 
@@ -297,31 +311,44 @@ __global__ void __launch_bounds__(128) convT_fp32_kernel(const ConvArgs a) {
 
 int fp32_conv_cout_tile(bool transposed) { return transposed ? CO_TT : CO_T; }
 
-int launch_conv_fp32(const ConvArgs& a, bool in_planar, int out_kind, cudaStream_t st) {
+template <typename T>
+static int launch_conv_t(const ConvArgs& a, bool in_planar, int out_kind, cudaStream_t st) {
   const int nt = ceil_div(a.od[2], 8) * ceil_div(a.od[1], 4) * ceil_div(a.od[0], 4 * PT);
   dim3 grid(nt, ceil_div(a.cout_groups * 8, CO_T), a.n);
   if (in_planar) {
     SGM_REQUIRE(out_kind == OUT_CG8, SGM_ERR_UNSUPPORTED, "planar-in conv writes CG8 only");
-    conv_fp32_kernel<true, OUT_CG8><<<grid, 128, 0, st>>>(a);
+    conv_fp32_kernel<T, true, OUT_CG8><<<grid, 128, 0, st>>>(a);
   } else if (out_kind == OUT_CG8) {
-    conv_fp32_kernel<false, OUT_CG8><<<grid, 128, 0, st>>>(a);
+    conv_fp32_kernel<T, false, OUT_CG8><<<grid, 128, 0, st>>>(a);
   } else if (out_kind == OUT_BLEND) {
-    conv_fp32_kernel<false, OUT_BLEND><<<grid, 128, 0, st>>>(a);
+    conv_fp32_kernel<T, false, OUT_BLEND><<<grid, 128, 0, st>>>(a);
   } else {
-    conv_fp32_kernel<false, OUT_PLANAR><<<grid, 128, 0, st>>>(a);
+    conv_fp32_kernel<T, false, OUT_PLANAR><<<grid, 128, 0, st>>>(a);
   }
   SGM_CUDA_CHECK(cudaGetLastError());
   return SGM_OK;
 }
 
-int launch_convT_fp32(const ConvArgs& a, cudaStream_t st) {
+int launch_conv_fp32(const ConvArgs& a, bool bf16_storage, bool in_planar, int out_kind, cudaStream_t st) {
+  return bf16_storage ? launch_conv_t<__nv_bfloat16>(a, in_planar, out_kind, st)
+                      : launch_conv_t<float>(a, in_planar, out_kind, st);
+}
+
+int launch_convT_fp32(const ConvArgs& a, bool bf16_storage, cudaStream_t st) {
   const bool flat0 = a.k[0] == 1;
   const int nt = ceil_div(a.id[2], 8) * ceil_div(a.id[1], 4) * ceil_div(a.id[0], 4);
   dim3 grid(nt, a.cout_groups, a.n);
-  if (flat0)
-    convT_fp32_kernel<true><<<grid, 128, 0, st>>>(a);
-  else
-    convT_fp32_kernel<false><<<grid, 128, 0, st>>>(a);
+  if (bf16_storage) {
+    if (flat0)
+      convT_fp32_kernel<__nv_bfloat16, true><<<grid, 128, 0, st>>>(a);
+    else
+      convT_fp32_kernel<__nv_bfloat16, false><<<grid, 128, 0, st>>>(a);
+  } else {
+    if (flat0)
+      convT_fp32_kernel<float, true><<<grid, 128, 0, st>>>(a);
+    else
+      convT_fp32_kernel<float, false><<<grid, 128, 0, st>>>(a);
+  }
   SGM_CUDA_CHECK(cudaGetLastError());
   return SGM_OK;
 }

@@ -50,7 +50,7 @@ namespace {
 // ---- fp32 packing: [coblk][cg][tap][ci 8][co CO_T], zero padded
 int pack_fp32(const sgm_conv_desc& d, PackedConv& pc, int spatial_dims) {
   const bool tr = pc.kind == SGM_KIND_CONV_TRANSPOSE;
-  const int co_t = fp32_conv_cout_tile(tr);
+  const int co_t = fp32_conv_cout_tile(tr && d.stride == 2);  // stride-1 convT runs as a flipped conv
   const int ntaps = pc.k[0] * pc.k[1] * pc.k[2];
   const int n_coblk = ceil_div(pc.cgout * 8, co_t);
   const size_t nw = (size_t)n_coblk * pc.cgin * ntaps * 8 * co_t;
@@ -116,8 +116,7 @@ int run_network(sgm_unet* net, const float* vol, long long vol_cstride, int vd1,
                 cudaStream_t st, bool dry) {
   const int L = net->n_levels;
   const size_t esz = net->precision == SGM_PRECISION_BF16 ? 2 : 4;
-  SGM_REQUIRE(net->precision == SGM_PRECISION_FP32, SGM_ERR_UNSUPPORTED,
-              "bf16 (tcgen05) network path is not wired into this build yet");
+  const bool bf16 = net->precision == SGM_PRECISION_BF16;
   auto alloc = [&](int cg, const int d[3]) {
     Tensor t;
     t.cg = cg;
@@ -156,8 +155,8 @@ int run_network(sgm_unet* net, const float* vol, long long vol_cstride, int vd1,
     a.out = out.p;
     a.res = res ? res->p : nullptr;
     net->last_launches++;
-    if (pc.kind == SGM_KIND_CONV_TRANSPOSE && pc.s[1] == 2) return launch_convT_fp32(a, st);
-    return launch_conv_fp32(a, false, OUT_CG8, st);
+    if (pc.kind == SGM_KIND_CONV_TRANSPOSE && pc.s[1] == 2) return launch_convT_fp32(a, bf16, st);
+    return launch_conv_fp32(a, bf16, false, OUT_CG8, st);
   };
 
   // level dims
@@ -191,7 +190,7 @@ int run_network(sgm_unet* net, const float* vol, long long vol_cstride, int vd1,
           a.out = which ? r.p : t.p;
           a.vol_cstride = vol_cstride, a.vd1 = vd1, a.vd2 = vd2, a.win_origin = win_origin_dev;
           net->last_launches++;
-          int rc = launch_conv_fp32(a, true, OUT_CG8, st);
+          int rc = launch_conv_fp32(a, bf16, true, OUT_CG8, st);
           if (rc) return rc;
         }
       }
@@ -258,7 +257,7 @@ int run_network(sgm_unet* net, const float* vol, long long vol_cstride, int vd1,
       if (head.kind == OUT_PLANAR) {
         a.res = u.p;
         net->last_launches++;
-        rc = launch_conv_fp32(a, false, OUT_PLANAR, st);
+        rc = launch_conv_fp32(a, bf16, false, OUT_PLANAR, st);
         if (rc) return rc;
       } else {
         for (int w = 0; w < n; ++w) {  // one launch per window: plain RMW, MONAI's window order
@@ -268,7 +267,7 @@ int run_network(sgm_unet* net, const float* vol, long long vol_cstride, int vd1,
           b.res = b.in0;
           b.wo[0] = head.wo_host[w * 3], b.wo[1] = head.wo_host[w * 3 + 1], b.wo[2] = head.wo_host[w * 3 + 2];
           net->last_launches++;
-          rc = launch_conv_fp32(b, false, OUT_BLEND, st);
+          rc = launch_conv_fp32(b, bf16, false, OUT_BLEND, st);
           if (rc) return rc;
         }
       }

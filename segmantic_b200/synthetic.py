@@ -60,6 +60,8 @@ def synthetic_state_dict(spatial_dims: int, in_channels: int, out_channels: int,
             t = torch.rand(shape, generator=g) * 0.3 + 0.1
         elif key.endswith("adn.N.weight"):
             t = torch.rand(shape, generator=g) + 0.5
+            if key.startswith("model.2.0."):  # top-level up-sampling: keep the logits O(1)
+                t = t * 0.12
         elif key.endswith("adn.N.bias"):
             t = torch.randn(shape, generator=g) * 0.1
         elif key.endswith("running_mean"):
