@@ -115,6 +115,17 @@ SGM_API int64_t sgm_unet_workspace_bytes(const sgm_unet* net, const int32_t roi[
 SGM_API int32_t sgm_unet_forward(sgm_unet* net, const float* x_dev, float* logits_dev, int32_t batch,
                          const int32_t roi[3], void* workspace_dev, int64_t workspace_bytes,
                          void* stream);
+/* Synchronises `stream` and reports a tcgen05 pipeline timeout raised by any earlier launch on this
+ * handle (the kernels bound every mbarrier wait instead of hanging the GPU). */
+SGM_API int32_t sgm_unet_check(sgm_unet* net, void* stream);
+/* Diagnostic: run convolution `conv_index` (canonical order) alone on caller-provided CG8 tensors
+ * ([n][cg][d0][d1][d2][8], fp32 or bf16 per the handle's precision), on the CUDA-core family
+ * (use_tc = 0) or the tcgen05 family (use_tc = 1; fused = 1 runs a strided down block's unit0 together
+ * with its residual-branch conv into out / out2).  Writes the output extent to out_dims. */
+SGM_API int32_t sgm_debug_conv(sgm_unet* net, int32_t conv_index, int32_t use_tc, int32_t fused,
+                               const void* in0, int32_t cg0, const void* in1, int32_t cg1, const void* res,
+                               void* out, void* out2, int32_t n, const int32_t in_dims[3],
+                               int32_t out_dims[3], void* stream);
 /* Number of kernel launches the last forward / sw_accumulate on this handle enqueued. */
 SGM_API int64_t sgm_unet_last_launch_count(const sgm_unet* net);
 

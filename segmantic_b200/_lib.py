@@ -62,6 +62,10 @@ SIGNATURES = {
     "sgm_unet_forward": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, _I3, C.c_void_p,
                                      C.c_int64, C.c_void_p]),
     "sgm_unet_last_launch_count": (C.c_int64, [C.c_void_p]),
+    "sgm_unet_check": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "sgm_debug_conv": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                   C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, _I3,
+                                   _I3, C.c_void_p]),
     "sgm_sw_accumulate": (C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(SwCfg), C.c_void_p, C.c_void_p,
                                       C.c_int64, C.c_void_p]),
     "sgm_sw_workspace_bytes": (C.c_int64, [C.c_void_p, C.POINTER(SwCfg)]),

@@ -1,0 +1,766 @@
+// tcgen05 implicit-GEMM convolutions for the MONAI UNet residual units (bf16 in, fp32 TMEM accumulate).
+//
+// Data layout.  Activations are CG8 bf16: [n][cg][d0][d1][d2][8 ch] -- one voxel's 8-channel group is
+// 16 bytes, and 8 consecutive d2 voxels of one group are 128 contiguous bytes: exactly one K-major
+// SWIZZLE_NONE "core matrix" (8 rows x 16 B) of a tcgen05 shared-memory descriptor.
+//
+// Algorithm.  A CTA stages the halo brick of its output tile ONCE in shared memory, as
+// [slab][cg][h0][h1][h2] x 16 B.  GEMM row m is a *padded linear* brick position p, so the A operand of
+// filter tap (k0,k1,k2) for 128 consecutive rows is the same brick read at p + shift(k): a descriptor
+// with start address + shift*16, SBO = 128 B (next 8 rows), LBO = one channel-group slab.  No im2col,
+// no per-tap reload: every tap / channel-pair is one MMA (M=128, N=Cout, K=16) straight from the brick.
+// Rows that fall in the halo are computed and discarded (tile shapes are chosen to keep them ~25 %).
+//   stride 2 (down path): the brick is loaded as 8 parity slabs (space-to-depth), taps pick slab+shift;
+//                         the residual-branch conv of the block reads the same A and is fused as extra N.
+//   transposed stride 2:  rows are INPUT voxels; the 8 output parity classes are 8 accumulators with
+//                         1/2/2/2/4/4/4/8 taps; A is the channel concat of skip and sub-network
+//                         tensors (two base pointers -- torch.cat is never materialised).
+// Warp roles (192 threads): warps 0-3 epilogue (TMEM -> regs -> bias/PReLU/residual -> bf16 CG8 store,
+// or fp32 importance-weighted accumulate into the volume for the head), warp 4 MMA issuer (one
+// thread), warp 5 weight producer (cp.async.bulk ring, mbarrier complete_tx).  The brick itself is
+// gathered by all threads with zero-filling cp.async (window-border zero padding for free).
+// Accumulators are double-buffered in TMEM so the epilogue of chunk i overlaps the MMAs of chunk i+1;
+// two CTAs per SM overlap brick loads with the other CTA's MMAs.
+#include "conv_tc.cuh"
+
+#include <algorithm>
+#include <string.h>
+
+namespace sgm {
+namespace tc {
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kSmemBudget = 110 * 1024;   // two CTAs per SM
+constexpr long long kWaitCycles = 4000000000LL;
+
+struct KArgs {
+  const __nv_bfloat16* in0;
+  const __nv_bfloat16* in1;
+  int cg0, cg1, cgin;
+  int id[3], od[3], rd[3];
+  int mode;
+  int t[3], H[3], lo[3], nt[3];
+  int ibase_mul[3];  // input coord = org*omul + ioff + imul*h + r  (see loader)
+  int imul[3], ioff[3], par[3];
+  int P, nslab;
+  int row_first, ntiles, tpc, nchunks, nbuf, ncls, cols_per_buf, tmem_cols;
+  int N, nblk, G, ngroups, nstages, resident;
+  const uint32_t* blkdesc;
+  const __nv_bfloat16* w;
+  const float* bias;
+  __nv_bfloat16* outA;
+  int cgA;
+  __nv_bfloat16* outB;
+  int cgB;
+  int segA_cg, actA;
+  float alphaA;
+  const __nv_bfloat16* res;
+  int out_kind;
+  float* pl_out;
+  long long pl_cstride, pl_nstride;
+  int ad0, ad1, ad2;
+  int wo[3];
+  const float* imap0;
+  const float* imap1;
+  const float* imap2;
+  float imap_floor;
+  int c_real;
+  int a_units;        // 16-byte units reserved for the A region
+  int w_stage_bytes;
+  int* error_flag;
+};
+
+// ------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must not hang the GPU.  Returns false (and raises the flag) on timeout.
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
+  if (mbar_try_wait(bar, parity)) return true;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > kWaitCycles) {
+      atomicExch(err, code);
+      return false;
+    }
+  }
+  return true;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                       uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t v[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) start>>4 | [16,30) LBO>>4 (next 16-byte K chunk) | [32,46) SBO>>4 (next 8-row group) | [46,48) version=1
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr16, uint32_t lbo16, uint32_t sbo16) {
+  const uint32_t lo = (addr16 & 0x3FFFu) | ((lbo16 & 0x3FFFu) << 16);
+  const uint32_t hi = (sbo16 & 0x3FFFu) | (1u << 14);
+  return ((uint64_t)hi << 32) | lo;
+}
+
+__device__ __forceinline__ float prelu(float v, float alpha) { return v > 0.f ? v : alpha * v; }
+
+__device__ __forceinline__ void unpack8(const uint4 v, float x[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    x[2 * i] = __uint_as_float(w[i] << 16);
+    x[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float v[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 b = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    w[i] = *reinterpret_cast<const uint32_t*>(&b);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// ------------------------------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const KArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int coblk = blockIdx.y, n = blockIdx.z;
+  int tile_lin = blockIdx.x;
+  const int b2 = tile_lin % a.nt[2];
+  tile_lin /= a.nt[2];
+  const int b1 = tile_lin % a.nt[1];
+  const int b0 = tile_lin / a.nt[1];
+  const int org[3] = {b0 * a.t[0], b1 * a.t[1], b2 * a.t[2]};  // tile origin in row space
+
+  uint8_t* a_smem = smem;
+  const int a_bytes = a.a_units * 16;
+  uint8_t* w_smem = smem + a_bytes;
+  int2* table = reinterpret_cast<int2*>(w_smem + a.nstages * a.w_stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(table) + ((a.nblk * 8 + 15) & ~15));
+  // bars: [0,nstages) wfull, [nstages,2nstages) wempty, then tfull[2], tempty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * a.nstages + 4);
+  const uint32_t bar0 = smem_u32(bars);
+  auto WFULL = [&](int s) { return bar0 + 8u * s; };
+  auto WEMPTY = [&](int s) { return bar0 + 8u * (a.nstages + s); };
+  auto TFULL = [&](int b) { return bar0 + 8u * (2 * a.nstages + b); };
+  auto TEMPTY = [&](int b) { return bar0 + 8u * (2 * a.nstages + 2 + b); };
+
+  if (warp == 4 && lane == 0) {
+    for (int s = 0; s < a.nstages; ++s) {
+      mbar_init(WFULL(s), 1);
+      mbar_init(WEMPTY(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(TFULL(b), 1);
+      mbar_init(TEMPTY(b), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)a.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+
+  // ---- K-block table: A start (16-byte units from the brick base) + class/first flags
+  const int H12 = a.H[1] * a.H[2];
+  for (int b = tid; b < a.nblk; b += kThreads) {
+    const uint32_t d = __ldg(a.blkdesc + b);
+    const int s0 = (int)(d & 3u) - 1, s1 = (int)((d >> 2) & 3u) - 1, s2 = (int)((d >> 4) & 3u) - 1;
+    const int slab = (d >> 6) & 7u, cls = (d >> 9) & 7u, first = (d >> 12) & 1u, cgpair = (d >> 16) & 0xffu;
+    const int a16 = (slab * a.cgin + cgpair * 2) * a.P + a.row_first + s0 * H12 + s1 * a.H[2] + s2;
+    table[b] = make_int2(a16, cls | (first << 8));
+  }
+
+  // ---- gather the halo brick: [slab][cg][P] x 16 B, zero fill outside the window
+  {
+    const long long ivox = (long long)a.id[0] * a.id[1] * a.id[2];
+    const int items = a.nslab * a.cgin * a.P;
+    const uint32_t a_base = smem_u32(a_smem);
+    const int ib0 = org[0] * a.ibase_mul[0] + a.ioff[0], ib1 = org[1] * a.ibase_mul[1] + a.ioff[1],
+              ib2 = org[2] * a.ibase_mul[2] + a.ioff[2];
+    for (int it = tid; it < items; it += kThreads) {
+      const int pos = it % a.P;
+      const int sc = it / a.P;
+      const int cg = sc % a.cgin, slab = sc / a.cgin;
+      const int h2 = pos % a.H[2];
+      const int h01 = pos / a.H[2];
+      const int h1 = h01 % a.H[1], h0 = h01 / a.H[1];
+      // parity bits of the slab, most significant = axis 0 (only axes with par==2 consume a bit)
+      int bits = slab;
+      const int r2 = a.par[2] == 2 ? (bits & 1) : 0;
+      bits >>= (a.par[2] == 2);
+      const int r1 = a.par[1] == 2 ? (bits & 1) : 0;
+      bits >>= (a.par[1] == 2);
+      const int r0 = a.par[0] == 2 ? (bits & 1) : 0;
+      const int i0 = ib0 + a.imul[0] * h0 + r0, i1 = ib1 + a.imul[1] * h1 + r1, i2 = ib2 + a.imul[2] * h2 + r2;
+      const bool ok = i0 >= 0 && i0 < a.id[0] && i1 >= 0 && i1 < a.id[1] && i2 >= 0 && i2 < a.id[2];
+      const __nv_bfloat16* src = a.in0;
+      if (ok) {
+        const long long ipos = ((long long)i0 * a.id[1] + i1) * a.id[2] + i2;
+        src = (cg < a.cg0) ? a.in0 + (((long long)n * a.cg0 + cg) * ivox + ipos) * 8
+                           : a.in1 + (((long long)n * a.cg1 + (cg - a.cg0)) * ivox + ipos) * 8;
+      }
+      cp_async16(a_base + (uint32_t)it * 16u, src, ok ? 16u : 0u);
+    }
+    // zero the tail the last M tile may read (keeps garbage rows finite; they are discarded anyway)
+    for (int it = items + tid; it < a.a_units; it += kThreads)
+      *reinterpret_cast<uint4*>(a_smem + (size_t)it * 16) = make_uint4(0, 0, 0, 0);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core reads
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int N = a.N;
+  if (warp == 5) {
+    // ================= weight producer: cp.async.bulk ring =================
+    if (lane == 0) {
+      const __nv_bfloat16* wsrc = a.w + (size_t)coblk * a.nblk * N * 16;
+      const int total = a.resident ? a.ngroups : a.nchunks * a.ngroups;
+      for (int it = 0; it < total; ++it) {
+        const int g = it % a.ngroups, stage = it % a.nstages;
+        if (it >= a.nstages) {
+          const uint32_t ph = (uint32_t)(it / a.nstages) & 1u;
+          if (!mbar_wait(WEMPTY(stage), ph ^ 1u, a.error_flag, 1)) break;
+        }
+        const int nb = min(a.G, a.nblk - g * a.G);
+        const uint32_t bytes = (uint32_t)nb * N * 32u;
+        mbar_expect_tx(WFULL(stage), bytes);
+        bulk_g2s(smem_u32(w_smem + (size_t)stage * a.w_stage_bytes), wsrc + (size_t)g * a.G * N * 16, bytes,
+                 WFULL(stage));
+      }
+    }
+  } else if (warp == 4) {
+    // ================= MMA issuer (single thread) =================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, K-major both, N>>3 at [17,23), M>>4 at [24,29)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t a_base16 = smem_u32(a_smem) >> 4;
+      const uint32_t w_base16 = smem_u32(w_smem) >> 4;
+      bool ok = true;
+      for (int chunk = 0; chunk < a.nchunks && ok; ++chunk) {
+        const int buf = a.nbuf == 2 ? (chunk & 1) : 0;
+        const int use = a.nbuf == 2 ? (chunk >> 1) : chunk;
+        if (use > 0) ok = mbar_wait(TEMPTY(buf), (uint32_t)(use - 1) & 1u, a.error_flag, 2);
+        if (!ok) break;
+        tc_fence_after();
+        const int tiles_here = min(a.tpc, a.ntiles - chunk * a.tpc);
+        for (int g = 0; g < a.ngroups && ok; ++g) {
+          int stage;
+          if (!a.resident || chunk == 0) {
+            const int it = a.resident ? g : chunk * a.ngroups + g;
+            stage = it % a.nstages;
+            ok = mbar_wait(WFULL(stage), (uint32_t)(it / a.nstages) & 1u, a.error_flag, 3);
+            if (!ok) break;
+            tc_fence_after();
+          } else {
+            stage = g;
+          }
+          const int bend = min(a.nblk, (g + 1) * a.G);
+          for (int b = g * a.G; b < bend; ++b) {
+            const int2 e = table[b];
+            const uint64_t bdesc =
+                make_desc(w_base16 + (uint32_t)(stage * a.w_stage_bytes + (b - g * a.G) * N * 32) / 16u, (uint32_t)N, 8u);
+            const uint32_t acc = (e.y >> 8) ? 0u : 1u;
+            const uint32_t col = (uint32_t)(buf * a.cols_per_buf + (e.y & 0xff) * N);
+            for (int t = 0; t < tiles_here; ++t) {
+              const uint64_t adesc =
+                  make_desc(a_base16 + (uint32_t)(e.x + (chunk * a.tpc + t) * 128), (uint32_t)a.P, 8u);
+              tc_mma(tmem_base + col + (uint32_t)(t * a.ncls * N), adesc, bdesc, idesc, acc);
+            }
+          }
+          if (!a.resident) tc_commit(WEMPTY(stage));
+        }
+        if (ok) tc_commit(TFULL(buf));
+      }
+    }
+  } else {
+    // ================= epilogue warps 0..3: TMEM lanes 32*warp .. 32*warp+31 =================
+    const long long ovox = (long long)a.od[0] * a.od[1] * a.od[2];
+    bool ok = true;
+    for (int chunk = 0; chunk < a.nchunks && ok; ++chunk) {
+      const int buf = a.nbuf == 2 ? (chunk & 1) : 0;
+      const int use = a.nbuf == 2 ? (chunk >> 1) : chunk;
+      ok = mbar_wait(TFULL(buf), (uint32_t)use & 1u, a.error_flag, 4);
+      if (!ok) break;
+      tc_fence_after();
+      const int tiles_here = min(a.tpc, a.ntiles - chunk * a.tpc);
+      for (int t = 0; t < tiles_here; ++t) {
+        const int p = a.row_first + (chunk * a.tpc + t) * 128 + warp * 32 + lane;
+        const int h2 = p % a.H[2];
+        const int h01 = p / a.H[2];
+        const int h1 = h01 % a.H[1], h0 = h01 / a.H[1];
+        const int r0 = org[0] + h0 - a.lo[0], r1 = org[1] + h1 - a.lo[1], r2 = org[2] + h2 - a.lo[2];
+        const bool valid = h0 >= a.lo[0] && h0 < a.lo[0] + a.t[0] && h1 >= a.lo[1] && h1 < a.lo[1] + a.t[1] &&
+                           h2 >= a.lo[2] && h2 < a.lo[2] + a.t[2] && r0 < a.rd[0] && r1 < a.rd[1] && r2 < a.rd[2];
+        for (int cls = 0; cls < a.ncls; ++cls) {
+          int o0 = r0, o1 = r1, o2 = r2;
+          if (a.mode == MODE_T2) {
+            int bits = cls;
+            o2 = 2 * r2 + (bits & 1);
+            bits >>= 1;
+            o1 = 2 * r1 + (bits & 1);
+            bits >>= 1;
+            o0 = a.par[0] == 2 ? 2 * r0 + (bits & 1) : r0;
+          }
+          const long long opos = ((long long)o0 * a.od[1] + o1) * a.od[2] + o2;
+          const uint32_t tcol =
+              tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * a.cols_per_buf + (t * a.ncls + cls) * N);
+          for (int piece = 0; piece < N / 16; ++piece) {
+            uint32_t raw[16];
+            tc_ld16(tcol + piece * 16, raw);  // warp-collective: every lane executes it
+            if (!valid) continue;
+            const int cbase = coblk * N + piece * 16;  // fused output channel of raw[0]
+            const int gcg = cbase >> 3;
+            const bool segA = gcg < a.segA_cg;
+            float v[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              float x = __uint_as_float(raw[c]) + __ldg(a.bias + cbase + c);
+              if (segA && a.actA) x = prelu(x, a.alphaA);
+              v[c] = x;
+            }
+            if (segA) {
+              if (a.res) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  float r[8];
+                  unpack8(__ldg(reinterpret_cast<const uint4*>(
+                              a.res + (((long long)n * a.cgA + gcg + h) * ovox + opos) * 8)),
+                          r);
+#pragma unroll
+                  for (int c = 0; c < 8; ++c) v[h * 8 + c] += r[c];
+                }
+              }
+              if (a.out_kind == OUT_CG8) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                  if (gcg + h < a.cgA)
+                    *reinterpret_cast<uint4*>(a.outA + (((long long)n * a.cgA + gcg + h) * ovox + opos) * 8) =
+                        pack8(v + h * 8);
+              } else {
+                long long off;
+                float imw = 1.f;
+                bool pl_ok = true;
+                if (a.out_kind == OUT_BLEND) {
+                  const int g0 = a.wo[0] + o0;
+                  pl_ok = g0 >= 0 && g0 < a.ad0;
+                  off = ((long long)g0 * a.ad1 + (a.wo[1] + o1)) * a.ad2 + (a.wo[2] + o2);
+                  imw = fmaxf(__fmul_rn(__fmul_rn(a.imap0[o0], a.imap1[o1]), a.imap2[o2]), a.imap_floor);
+                } else {
+                  off = (long long)n * a.pl_nstride + opos;
+                }
+                if (pl_ok) {
+#pragma unroll
+                  for (int c = 0; c < 16; ++c) {
+                    const int ch = cbase + c;
+                    if (ch < a.c_real) {
+                      float* dst = a.pl_out + ch * a.pl_cstride + off;
+                      if (a.out_kind == OUT_BLEND)
+                        *dst = __fadd_rn(*dst, __fmul_rn(v[c], imw));
+                      else
+                        *dst = v[c];
+                    }
+                  }
+                }
+              }
+            } else {
+              const int bcg = gcg - a.segA_cg;
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+                if (bcg + h < a.cgB)
+                  *reinterpret_cast<uint4*>(a.outB + (((long long)n * a.cgB + bcg + h) * ovox + opos) * 8) =
+                      pack8(v + h * 8);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(TEMPTY(buf));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------- host
+inline uint16_t f2bf(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7f800000u) != 0x7f800000u) u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+bool tc_supported(const sgm_conv_desc& d) {
+  if (d.kind == SGM_KIND_IDENTITY) return false;
+  if (d.cin < 16 && d.cin % 8 != 0) return false;  // the 1..8-channel stem stays on CUDA cores
+  return (d.kernel == 3 || d.kernel == 1) && (d.stride == 1 || d.stride == 2);
+}
+
+struct BlkCache {
+  const TcConv* key;
+  uint32_t* dev;
+};
+static std::vector<BlkCache> g_blk_cache;
+
+void tc_free(TcConv* c) {
+  if (!c) return;
+  for (size_t i = 0; i < g_blk_cache.size(); ++i)
+    if (g_blk_cache[i].key == c) {
+      cudaFree(g_blk_cache[i].dev);
+      g_blk_cache.erase(g_blk_cache.begin() + i);
+      break;
+    }
+  if (c->w) cudaFree(c->w);
+  if (c->bias) cudaFree(c->bias);
+  delete c;
+}
+
+// Weight element of the (possibly flipped / transposed) conv: W(co, ci, tap)
+static inline float wget(const sgm_conv_desc& d, int co, int ci, int tap, int ntaps) {
+  if (d.kind == SGM_KIND_CONV_TRANSPOSE) {
+    const int t = d.stride == 1 ? (ntaps - 1 - tap) : tap;  // stride-1 transposed conv == flipped conv
+    return d.weight[((size_t)ci * d.cout + co) * ntaps + t];
+  }
+  return d.weight[((size_t)co * d.cin + ci) * ntaps + tap];
+}
+
+int tc_pack(const sgm_conv_desc* m, const sgm_conv_desc* second, int spatial_dims, TcConv** out) {
+  *out = nullptr;
+  SGM_REQUIRE(m && tc_supported(*m), SGM_ERR_UNSUPPORTED, "conv not supported by the tcgen05 family");
+  TcConv* c = new TcConv();
+  const bool tr2 = m->kind == SGM_KIND_CONV_TRANSPOSE && m->stride == 2;
+  c->mode = tr2 ? MODE_T2 : (m->stride == 2 ? MODE_S2 : MODE_S1);
+  c->flat0 = spatial_dims == 2;
+  c->cin = m->cin;
+  c->cgin = round_up(m->cin, 16) / 8;
+  for (int a = 0; a < 3; ++a) c->k[a] = (c->flat0 && a == 0) ? 1 : m->kernel;
+  const int ntaps = c->k[0] * c->k[1] * c->k[2];
+  const int nA = round_up(m->cout, 16);
+  int nB = 0;
+  if (second) {
+    if (second->kind != SGM_KIND_CONV || second->kernel != m->kernel || second->stride != m->stride ||
+        second->cin != m->cin || m->kind != SGM_KIND_CONV) {
+      delete c;
+      set_error("tc_pack: second conv cannot be fused (different geometry)");
+      return SGM_ERR_INVALID;
+    }
+    nB = round_up(second->cout, 16);
+  }
+  c->ntot = nA + nB;
+  c->segA_cg = nA / 8;
+  c->actA = m->has_act;
+  c->alphaA = m->alpha;
+  c->c_real = m->cout;
+  c->ncls = tr2 ? (c->flat0 ? 4 : 8) : 1;
+  // output channels per CTA: multiple of 16 dividing ntot; TMEM: ncls * N <= 256 columns
+  const int cap = tr2 ? std::max(16, 256 / c->ncls) : 128;
+  int N = 16;
+  for (int cand = 16; cand <= std::min(cap, c->ntot); cand += 16)
+    if (c->ntot % cand == 0) N = cand;
+  c->ncta = N;
+  c->ncoblk = c->ntot / N;
+
+  // ---- K blocks
+  const int ncgp = c->cgin / 2;
+  if (c->mode == MODE_S1) {
+    for (int k0 = 0; k0 < c->k[0]; ++k0)
+      for (int k1 = 0; k1 < c->k[1]; ++k1)
+        for (int k2 = 0; k2 < c->k[2]; ++k2)
+          for (int p = 0; p < ncgp; ++p) {
+            KBlock b{0, p, {k0 - c->k[0] / 2, k1 - c->k[1] / 2, k2 - c->k[2] / 2}, 0, c->blocks.empty() ? 1 : 0};
+            c->blocks.push_back(b);
+          }
+  } else if (c->mode == MODE_S2) {
+    auto pe = [](int K, int k, int& r, int& e) {  // i = 2o + k - 1 = 2(o+e) + r
+      if (K == 1) { r = 0; e = 0; return; }
+      if (k == 0) { r = 1; e = -1; } else if (k == 1) { r = 0; e = 0; } else { r = 1; e = 0; }
+    };
+    for (int k0 = 0; k0 < c->k[0]; ++k0)
+      for (int k1 = 0; k1 < c->k[1]; ++k1)
+        for (int k2 = 0; k2 < c->k[2]; ++k2) {
+          int r0, e0, r1, e1, r2, e2;
+          pe(c->k[0], k0, r0, e0), pe(c->k[1], k1, r1, e1), pe(c->k[2], k2, r2, e2);
+          const int slab = c->flat0 ? (r1 * 2 + r2) : (r0 * 4 + r1 * 2 + r2);
+          for (int p = 0; p < ncgp; ++p) {
+            KBlock b{slab, p, {e0, e1, e2}, 0, c->blocks.empty() ? 1 : 0};
+            c->blocks.push_back(b);
+          }
+        }
+  } else {
+    // o = 2j + p reads in[j + sh] * W[k]:  p=0: (sh 0, k 1);  p=1: (sh 0, k 2), (sh 1, k 0)
+    const int np0 = c->flat0 ? 1 : 2;
+    for (int p0 = 0; p0 < np0; ++p0)
+      for (int p1 = 0; p1 < 2; ++p1)
+        for (int p2 = 0; p2 < 2; ++p2) {
+          const int cls = c->flat0 ? (p1 * 2 + p2) : (p0 * 4 + p1 * 2 + p2);
+          bool first = true;
+          for (int sh0 = 0; sh0 <= (c->flat0 ? 0 : p0); ++sh0)
+            for (int sh1 = 0; sh1 <= p1; ++sh1)
+              for (int sh2 = 0; sh2 <= p2; ++sh2)
+                for (int p = 0; p < ncgp; ++p) {
+                  KBlock b{0, p, {sh0, sh1, sh2}, cls, first ? 1 : 0};
+                  first = false;
+                  c->blocks.push_back(b);
+                }
+        }
+  }
+  const int nblk = (int)c->blocks.size();
+
+  // ---- weights: [coblk][blk][kchunk 2][N][8] bf16
+  std::vector<uint16_t> w((size_t)c->ncoblk * nblk * 2 * N * 8, 0);
+  std::vector<float> bias(c->ntot, 0.f);
+  for (int co = 0; co < m->cout; ++co) bias[co] = m->bias[co];
+  if (second)
+    for (int co = 0; co < second->cout; ++co) bias[nA + co] = second->bias[co];
+  auto tap_of = [&](const KBlock& b) -> int {
+    int kk[3];
+    for (int a = 0; a < 3; ++a) {
+      if (c->k[a] == 1) { kk[a] = 0; continue; }
+      if (c->mode == MODE_S1) kk[a] = b.shift[a] + 1;
+      else if (c->mode == MODE_S2) {
+        // recover k from (r, e): slab bit r, shift e
+        int bit;
+        if (c->flat0) bit = a == 1 ? (b.slab >> 1) & 1 : (b.slab & 1);
+        else bit = (b.slab >> (2 - a)) & 1;
+        kk[a] = bit == 0 ? 1 : (b.shift[a] == -1 ? 0 : 2);
+      } else {
+        int pbit;
+        if (c->flat0) pbit = a == 1 ? (b.cls >> 1) & 1 : (b.cls & 1);
+        else pbit = (b.cls >> (2 - a)) & 1;
+        kk[a] = pbit == 0 ? 1 : (b.shift[a] == 0 ? 2 : 0);
+      }
+    }
+    return (kk[0] * c->k[1] + kk[1]) * c->k[2] + kk[2];
+  };
+  for (int cb = 0; cb < c->ncoblk; ++cb)
+    for (int bi = 0; bi < nblk; ++bi) {
+      const KBlock& b = c->blocks[bi];
+      const int tap = tap_of(b);
+      for (int kc = 0; kc < 2; ++kc)
+        for (int nn = 0; nn < N; ++nn) {
+          const int fco = cb * N + nn;  // fused output channel
+          const sgm_conv_desc* src = fco < nA ? m : second;
+          const int co = fco < nA ? fco : fco - nA;
+          if (!src || co >= src->cout) continue;
+          for (int k8 = 0; k8 < 8; ++k8) {
+            const int ci = (b.cgpair * 2 + kc) * 8 + k8;
+            if (ci >= m->cin) continue;
+            w[((((size_t)cb * nblk + bi) * 2 + kc) * N + nn) * 8 + k8] = f2bf(wget(*src, co, ci, tap, ntaps));
+          }
+        }
+    }
+  if (cudaMalloc(&c->w, w.size() * 2) != cudaSuccess || cudaMalloc(&c->bias, bias.size() * 4) != cudaSuccess) {
+    set_error("tc_pack: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+    tc_free(c);
+    return SGM_ERR_CUDA;
+  }
+  cudaMemcpy(c->w, w.data(), w.size() * 2, cudaMemcpyHostToDevice);
+  cudaMemcpy(c->bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice);
+  *out = c;
+  return SGM_OK;
+}
+
+// Device copy of the block descriptors: a small side allocation created lazily (one per conv).
+static uint32_t* blkdesc_dev(const TcConv& c) {
+  for (auto& e : g_blk_cache)
+    if (e.key == &c) return e.dev;
+  std::vector<uint32_t> d(c.blocks.size());
+  for (size_t i = 0; i < d.size(); ++i) {
+    const KBlock& b = c.blocks[i];
+    d[i] = (uint32_t)(b.shift[0] + 1) | ((uint32_t)(b.shift[1] + 1) << 2) | ((uint32_t)(b.shift[2] + 1) << 4) |
+           ((uint32_t)b.slab << 6) | ((uint32_t)b.cls << 9) | ((uint32_t)b.first << 12) | ((uint32_t)b.cgpair << 16);
+  }
+  uint32_t* dev = nullptr;
+  if (cudaMalloc(&dev, d.size() * 4) != cudaSuccess) return nullptr;
+  cudaMemcpy(dev, d.data(), d.size() * 4, cudaMemcpyHostToDevice);
+  g_blk_cache.push_back({&c, dev});
+  return dev;
+}
+
+int tc_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t st) {
+  KArgs a;
+  memset(&a, 0, sizeof(a));
+  SGM_REQUIRE(io.cg0 + io.cg1 == c.cgin, SGM_ERR_INVALID, "tc_launch: input channel groups %d+%d != %d", io.cg0,
+              io.cg1, c.cgin);
+  a.in0 = (const __nv_bfloat16*)io.in0, a.in1 = (const __nv_bfloat16*)io.in1;
+  a.cg0 = io.cg0, a.cg1 = io.cg1, a.cgin = c.cgin;
+  a.mode = c.mode;
+  for (int i = 0; i < 3; ++i) {
+    a.id[i] = io.id[i], a.od[i] = io.od[i];
+    a.rd[i] = c.mode == MODE_T2 ? io.id[i] : io.od[i];
+  }
+  const int N = c.ncta, nblk = (int)c.blocks.size();
+  a.N = N, a.nblk = nblk, a.ncls = c.ncls;
+  // weight ring
+  a.G = std::max(1, std::min(nblk, 16384 / (N * 32)));
+  a.ngroups = ceil_div(nblk, a.G);
+  a.nstages = std::min(3, a.ngroups);
+  a.resident = a.ngroups <= a.nstages;
+  a.w_stage_bytes = round_up(a.G * N * 32, 128);
+  // TMEM
+  int cols_tile = c.ncls * N;
+  a.nbuf = cols_tile <= 128 ? 2 : 1;
+  a.tpc = std::max(1, (a.nbuf == 2 ? 128 : 256) / cols_tile);
+  SGM_REQUIRE(cols_tile <= 256, SGM_ERR_UNSUPPORTED, "tc_launch: %d TMEM columns per tile", cols_tile);
+
+  // ---- per-axis geometry of the brick
+  int pad[3], addH[3];
+  for (int i = 0; i < 3; ++i) {
+    const bool flat = c.k[i] == 1 && (c.flat0 && i == 0);
+    pad[i] = c.k[i] / 2;
+    if (c.mode == MODE_S1) {
+      a.par[i] = 1, a.lo[i] = pad[i], addH[i] = 2 * pad[i];
+      a.ibase_mul[i] = 1, a.ioff[i] = -pad[i], a.imul[i] = 1;
+    } else if (c.mode == MODE_S2) {
+      if (flat || c.k[i] == 1) {
+        a.par[i] = 1, a.lo[i] = 0, addH[i] = 0, a.ibase_mul[i] = 1, a.ioff[i] = 0, a.imul[i] = 1;
+      } else {
+        a.par[i] = 2, a.lo[i] = 1, addH[i] = 1, a.ibase_mul[i] = 2, a.ioff[i] = -2, a.imul[i] = 2;
+      }
+    } else {
+      if (flat) {
+        a.par[i] = 1, a.lo[i] = 0, addH[i] = 0;
+      } else {
+        a.par[i] = 2, a.lo[i] = 0, addH[i] = 1;  // par==2 marks "output = 2*row + class bit"
+      }
+      a.ibase_mul[i] = 1, a.ioff[i] = 0, a.imul[i] = 1;
+    }
+  }
+  a.nslab = 1;
+  if (c.mode == MODE_S2)
+    for (int i = 0; i < 3; ++i) a.nslab *= a.par[i];
+
+  // ---- tile shape search (cost model: MMA issue cycles + brick bytes, times waves)
+  static const int cand[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64, 96};
+  double best = 1e30;
+  int bt[3] = {0, 0, 0};
+  const int fixed_bytes = a.nstages * a.w_stage_bytes + round_up(nblk * 8, 16) + (2 * a.nstages + 4) * 8 + 16 + 256;
+  for (int c0 : cand)
+    for (int c1 : cand)
+      for (int c2 : cand) {
+        const int t[3] = {std::min(c0, a.rd[0]), std::min(c1, a.rd[1]), std::min(c2, a.rd[2])};
+        const int H[3] = {t[0] + addH[0], t[1] + addH[1], t[2] + addH[2]};
+        const int P = H[0] * H[1] * H[2];
+        if (P > 16383) continue;
+        const int rf = (a.lo[0] * H[1] + a.lo[1]) * H[2] + a.lo[2];
+        const int rl = ((a.lo[0] + t[0] - 1) * H[1] + a.lo[1] + t[1] - 1) * H[2] + a.lo[2] + t[2] - 1;
+        const int ntl = ceil_div(rl - rf + 1, 128);
+        const int units = a.nslab * c.cgin * P + 128 + 2 * (H[1] * H[2] + H[2] + 2);
+        if ((long long)units * 16 + fixed_bytes > kSmemBudget) continue;
+        const long long nct = (long long)ceil_div(a.rd[0], t[0]) * ceil_div(a.rd[1], t[1]) * ceil_div(a.rd[2], t[2]) *
+                              c.ncoblk * io.n;
+        const double mma = (double)ntl * nblk * (32.0 + N / 4.0);
+        const double load = (double)a.nslab * c.cgin * P * 16 / 24.0;
+        const double epi = (double)ntl * c.ncls * (N / 16) * 60.0;
+        const double cta = std::max(mma, epi) + load + 4000.0;
+        const double waves = (double)((nct + 295) / 296);
+        const double cost = waves * cta;
+        if (cost < best) best = cost, bt[0] = t[0], bt[1] = t[1], bt[2] = t[2];
+      }
+  SGM_REQUIRE(bt[0] > 0, SGM_ERR_UNSUPPORTED, "tc_launch: no tile shape fits shared memory (cgin=%d, N=%d)", c.cgin, N);
+  for (int i = 0; i < 3; ++i) {
+    a.t[i] = bt[i];
+    a.H[i] = bt[i] + addH[i];
+    a.nt[i] = ceil_div(a.rd[i], bt[i]);
+  }
+  a.P = a.H[0] * a.H[1] * a.H[2];
+  a.row_first = (a.lo[0] * a.H[1] + a.lo[1]) * a.H[2] + a.lo[2];
+  const int row_last = ((a.lo[0] + a.t[0] - 1) * a.H[1] + a.lo[1] + a.t[1] - 1) * a.H[2] + a.lo[2] + a.t[2] - 1;
+  a.ntiles = ceil_div(row_last - a.row_first + 1, 128);
+  a.tpc = std::min(a.tpc, a.ntiles);
+  a.nchunks = ceil_div(a.ntiles, a.tpc);
+  a.cols_per_buf = a.tpc * cols_tile;
+  int cols = a.nbuf * a.cols_per_buf, pw = 32;
+  while (pw < cols) pw <<= 1;
+  a.tmem_cols = pw;
+  a.a_units = a.nslab * c.cgin * a.P + 128 + 2 * (a.H[1] * a.H[2] + a.H[2] + 2);
+  a.a_units = round_up(a.a_units, 8);
+  const int smem_bytes = a.a_units * 16 + fixed_bytes;
+
+  a.blkdesc = blkdesc_dev(c);
+  SGM_REQUIRE(a.blkdesc, SGM_ERR_CUDA, "tc_launch: block table upload failed");
+  a.w = c.w, a.bias = c.bias;
+  a.outA = (__nv_bfloat16*)io.outA, a.cgA = io.cgA, a.outB = (__nv_bfloat16*)io.outB, a.cgB = io.cgB;
+  a.segA_cg = c.segA_cg, a.actA = c.actA, a.alphaA = c.alphaA;
+  a.res = (const __nv_bfloat16*)io.res;
+  a.out_kind = io.out_kind, a.pl_out = io.pl_out, a.pl_cstride = io.pl_cstride, a.pl_nstride = io.pl_nstride;
+  a.ad0 = io.ad0, a.ad1 = io.ad1, a.ad2 = io.ad2;
+  for (int i = 0; i < 3; ++i) a.wo[i] = io.wo[i];
+  a.imap0 = io.imap[0], a.imap1 = io.imap[1], a.imap2 = io.imap[2], a.imap_floor = io.imap_floor;
+  a.c_real = c.c_real;
+  a.error_flag = error_flag_dev;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    SGM_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    attr_set = true;
+  }
+  dim3 grid(a.nt[0] * a.nt[1] * a.nt[2], c.ncoblk, io.n);
+  tc_conv_kernel<<<grid, kThreads, smem_bytes, st>>>(a);
+  SGM_CUDA_CHECK(cudaGetLastError());
+  return SGM_OK;
+}
+
+}  // namespace tc
+}  // namespace sgm

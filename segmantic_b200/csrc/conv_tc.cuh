@@ -1,0 +1,71 @@
+// tcgen05 implicit-GEMM convolution family (bf16 operands, fp32 accumulation in TMEM), sm_100a.
+#pragma once
+#include "common.cuh"
+
+#include <vector>
+
+namespace sgm {
+namespace tc {
+
+enum { MODE_S1 = 0, MODE_S2 = 1, MODE_T2 = 2 };
+
+// One K=16 step of the implicit GEMM: which 16-byte-row view of the shared-memory activation
+// slab is the A operand, and which accumulator (output parity class) it feeds.
+struct KBlock {
+  int slab;      // parity slab (S2) or 0
+  int cgpair;    // pair of input channel groups (16 channels)
+  int shift[3];  // row-space shift per axis
+  int cls;       // accumulator class (T2) or 0
+  int first;     // first block of its class -> overwrite instead of accumulate
+};
+
+// Device-resident, per-convolution packing for the tcgen05 family.
+struct TcConv {
+  int mode = MODE_S1;
+  int cin = 0, cgin = 0;      // cgin even (channels padded to 16)
+  int ntot = 0;               // fused output channels, padded to 16 (main [+ residual branch])
+  int ncta = 0;               // output channels per CTA (MMA N)
+  int ncoblk = 0;
+  int k[3] = {3, 3, 3};       // kernel extent per axis (1 on the flat axis of 2-D networks)
+  int flat0 = 0;              // 2-D network: axis 0 has extent 1, kernel 1, stride 1
+  int ncls = 1;
+  std::vector<KBlock> blocks; // host copy, in weight-pack order
+  __nv_bfloat16* w = nullptr; // device [ncoblk][nblk][2][ncta][8]
+  float* bias = nullptr;      // device [ntot]
+  // epilogue segments in units of output channel groups of the fused N
+  int segA_cg = 0;            // first segA_cg groups -> out A (act_a / alpha_a), rest -> out B (no act)
+  int actA = 0;
+  float alphaA = 0.f;
+  int c_real = 0;             // real (unpadded) channels of segment A
+};
+
+struct TcIO {
+  const void* in0 = nullptr;  // bf16 CG8
+  const void* in1 = nullptr;
+  int cg0 = 0, cg1 = 0;
+  int n = 1;
+  int id[3] = {1, 1, 1};
+  int od[3] = {1, 1, 1};
+  void* outA = nullptr;       // bf16 CG8 [n][cgA][od]
+  int cgA = 0;
+  void* outB = nullptr;       // bf16 CG8 [n][cgB][od] (fused residual branch) or nullptr
+  int cgB = 0;
+  const void* res = nullptr;  // bf16 CG8 residual added to segment A after the activation
+  int out_kind = OUT_CG8;     // OUT_CG8 | OUT_BLEND | OUT_PLANAR (segment A only)
+  float* pl_out = nullptr;
+  long long pl_cstride = 0, pl_nstride = 0;
+  int ad0 = 0, ad1 = 0, ad2 = 0;
+  int wo[3] = {0, 0, 0};
+  const float* imap[3] = {nullptr, nullptr, nullptr};
+  float imap_floor = 0.f;
+};
+
+// Build the packing for a convolution (optionally fused with a second conv reading the same input).
+// `main` and `second` are folded fp32 descriptors; `second` may be null.
+int tc_pack(const sgm_conv_desc* main_desc, const sgm_conv_desc* second, int spatial_dims, TcConv** out);
+void tc_free(TcConv* c);
+bool tc_supported(const sgm_conv_desc& d);
+int tc_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t st);
+
+}  // namespace tc
+}  // namespace sgm

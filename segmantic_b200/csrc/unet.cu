@@ -1,8 +1,10 @@
 // sgm_unet handle: weight packing, the per-window-batch layer program, and the C ABI for
 // Net.forward (seg/monai_unet.py:221-222) and the sliding-window inferer (seg/monai_unet.py:637-665).
 #include "common.cuh"
+#include "conv_tc.cuh"
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -29,8 +31,10 @@ struct PackedConv {
   int k[3] = {1, 1, 1}, s[3] = {1, 1, 1}, pad[3] = {0, 0, 0};
   int act = 0;
   float alpha = 0.f;
-  float* w32 = nullptr;   // fp32 family packing
+  float* w32 = nullptr;   // CUDA-core family packing
   float* bias = nullptr;  // [cgout*8] (padded to the cout tile)
+  tc::TcConv* tc = nullptr;        // tcgen05 packing of this conv (bf16 precision)
+  tc::TcConv* tc_fused = nullptr;  // unit0 of a strided down block fused with its residual-branch conv
 };
 
 }  // namespace sgm
@@ -41,14 +45,28 @@ struct sgm_unet {
   int precision = SGM_PRECISION_FP32;
   std::vector<sgm::PackedConv> convs;
   int64_t last_launches = 0;
+  // tcgen05 dispatch mask (env SGM_TC, default all): 1 stride-1 convs, 2 strided down convs (fused
+  // with the residual branch), 4 transposed convs, 8 head (conv + blend epilogue)
+  int tc_mask = 15;
+  int* err_dev = nullptr;  // device flag raised by a tcgen05 pipeline timeout
 };
 
 namespace sgm {
 
 namespace {
 
-// ---- fp32 packing: [coblk][cg][tap][ci 8][co CO_T], zero padded
-int pack_fp32(const sgm_conv_desc& d, PackedConv& pc, int spatial_dims) {
+// round-to-nearest-even fp32 -> bf16 -> fp32 (host)
+inline float bf16_round(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7f800000u) != 0x7f800000u) u += 0x7fffu + ((u >> 16) & 1u);
+  u &= 0xffff0000u;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+// ---- CUDA-core packing: [coblk][cg][tap][ci 8][co CO_T], zero padded (bf16 path: bf16-rounded values)
+int pack_fp32(const sgm_conv_desc& d, PackedConv& pc, bool round_bf16) {
   const bool tr = pc.kind == SGM_KIND_CONV_TRANSPOSE;
   const int co_t = fp32_conv_cout_tile(tr && d.stride == 2);  // stride-1 convT runs as a flipped conv
   const int ntaps = pc.k[0] * pc.k[1] * pc.k[2];
@@ -65,10 +83,9 @@ int pack_fp32(const sgm_conv_desc& d, PackedConv& pc, int spatial_dims) {
         const float v = tr ? d.weight[((size_t)ci * pc.cout + co) * ntaps + st]
                            : d.weight[((size_t)co * pc.cin + ci) * ntaps + st];
         const size_t dst = ((((size_t)(co / co_t) * pc.cgin + ci / 8) * ntaps + t) * 8 + ci % 8) * co_t + co % co_t;
-        w[dst] = v;
+        w[dst] = round_bf16 ? bf16_round(v) : v;
       }
   }
-  (void)spatial_dims;
   if (cudaMalloc(&pc.w32, nw * sizeof(float)) != cudaSuccess ||
       cudaMalloc(&pc.bias, b.size() * sizeof(float)) != cudaSuccess) {
     set_error("cudaMalloc of packed weights failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -140,23 +157,64 @@ int run_network(sgm_unet* net, const float* vol, long long vol_cstride, int vd1,
     a.c_real = pc.cout;
     return a;
   };
-  auto conv = [&](const PackedConv& pc, const Tensor& in0, const Tensor* in1, Tensor& out,
-                  const Tensor* res) -> int {
-    int od[3];
+  auto tc_bit = [&](const PackedConv& pc) {
+    if (!pc.tc) return 0;
+    return pc.tc->mode == tc::MODE_S1 ? 1 : (pc.tc->mode == tc::MODE_S2 ? 2 : 4);
+  };
+  auto conv_dims = [&](const PackedConv& pc, const Tensor& in0, int od[3]) {
     if (pc.kind == SGM_KIND_CONV_TRANSPOSE && pc.s[1] == 2) {
       for (int i = 0; i < 3; ++i) od[i] = in0.d[i] * pc.s[i];
     } else {
       for (int i = 0; i < 3; ++i) od[i] = out_dim(in0.d[i], pc.k[i], pc.s[i], pc.pad[i]);
     }
+  };
+  auto tc_io = [&](const Tensor& in0, const Tensor* in1, const int od[3]) {
+    tc::TcIO io;
+    io.in0 = in0.p, io.cg0 = in0.cg;
+    io.in1 = in1 ? in1->p : nullptr, io.cg1 = in1 ? in1->cg : 0;
+    io.n = n;
+    for (int i = 0; i < 3; ++i) io.id[i] = in0.d[i], io.od[i] = od[i];
+    return io;
+  };
+  auto conv = [&](const PackedConv& pc, const Tensor& in0, const Tensor* in1, Tensor& out,
+                  const Tensor* res) -> int {
+    int od[3];
+    conv_dims(pc, in0, od);
     out = alloc(pc.cgout, od);
     if (dry) return SGM_OK;
     SGM_REQUIRE(in0.cg + (in1 ? in1->cg : 0) == pc.cgin, SGM_ERR_INVALID, "channel-group mismatch");
+    net->last_launches++;
+    if (bf16 && (net->tc_mask & tc_bit(pc))) {
+      tc::TcIO io = tc_io(in0, in1, od);
+      io.outA = out.p, io.cgA = out.cg, io.res = res ? res->p : nullptr;
+      return tc::tc_launch(*pc.tc, io, net->err_dev, st);
+    }
     ConvArgs a = base_args(pc, in0, in1, od);
     a.out = out.p;
     a.res = res ? res->p : nullptr;
-    net->last_launches++;
     if (pc.kind == SGM_KIND_CONV_TRANSPOSE && pc.s[1] == 2) return launch_convT_fp32(a, bf16, st);
     return launch_conv_fp32(a, bf16, false, OUT_CG8, st);
+  };
+  // unit0 + residual-branch conv of a strided down block: same input, one fused tcgen05 launch
+  auto conv_pair = [&](const PackedConv& u0, const PackedConv& rs, const Tensor& in0, Tensor& t, Tensor& r) -> int {
+    if (bf16 && u0.tc_fused && (net->tc_mask & 2)) {
+      int od[3];
+      conv_dims(u0, in0, od);
+      t = alloc(u0.cgout, od);
+      r = alloc(rs.cgout, od);
+      if (dry) return SGM_OK;
+      net->last_launches++;
+      tc::TcIO io = tc_io(in0, nullptr, od);
+      io.outA = t.p, io.cgA = t.cg, io.outB = r.p, io.cgB = r.cg;
+      return tc::tc_launch(*u0.tc_fused, io, net->err_dev, st);
+    }
+    int rc = conv(u0, in0, nullptr, t, nullptr);
+    if (rc) return rc;
+    if (rs.kind == SGM_KIND_IDENTITY) {
+      r = in0;
+      return SGM_OK;
+    }
+    return conv(rs, in0, nullptr, r, nullptr);
   };
 
   // level dims
@@ -195,14 +253,8 @@ int run_network(sgm_unet* net, const float* vol, long long vol_cstride, int vd1,
         }
       }
     } else {
-      int rc = conv(u0, cur, nullptr, t, nullptr);
+      int rc = conv_pair(u0, rs, cur, t, r);
       if (rc) return rc;
-      if (rs.kind == SGM_KIND_IDENTITY) {
-        r = cur;
-      } else {
-        rc = conv(rs, cur, nullptr, r, nullptr);
-        if (rc) return rc;
-      }
     }
     int rc = conv(u1, t, nullptr, x, &r);
     if (rc) return rc;
@@ -249,25 +301,43 @@ int run_network(sgm_unet* net, const float* vol, long long vol_cstride, int vd1,
       if (dry) break;
       // head: conv C->C (conv only) + identity residual -> planar logits / blended accumulator
       const long long uvox = u.vox();
+      const bool head_tc = bf16 && ru.tc && (net->tc_mask & 8);
       ConvArgs a = base_args(ru, u, nullptr, u.d);
       a.pl_out = head.out, a.pl_cstride = head.cstride, a.pl_nstride = head.nstride;
       a.ad0 = head.ad0, a.ad1 = head.ad1, a.ad2 = head.ad2;
       a.imap0 = head.imap[0], a.imap1 = head.imap[1], a.imap2 = head.imap[2];
       a.imap_floor = head.floor;
+      tc::TcIO io = tc_io(u, nullptr, u.d);
+      io.cgA = u.cg;
+      io.pl_out = head.out, io.pl_cstride = head.cstride, io.pl_nstride = head.nstride;
+      io.ad0 = head.ad0, io.ad1 = head.ad1, io.ad2 = head.ad2;
+      for (int q = 0; q < 3; ++q) io.imap[q] = head.imap[q];
+      io.imap_floor = head.floor;
       if (head.kind == OUT_PLANAR) {
-        a.res = u.p;
         net->last_launches++;
-        rc = launch_conv_fp32(a, bf16, false, OUT_PLANAR, st);
+        if (head_tc) {
+          io.res = u.p, io.out_kind = OUT_PLANAR;
+          rc = tc::tc_launch(*ru.tc, io, net->err_dev, st);
+        } else {
+          a.res = u.p;
+          rc = launch_conv_fp32(a, bf16, false, OUT_PLANAR, st);
+        }
         if (rc) return rc;
       } else {
         for (int w = 0; w < n; ++w) {  // one launch per window: plain RMW, MONAI's window order
-          ConvArgs b = a;
-          b.n = 1;
-          b.in0 = reinterpret_cast<const char*>(u.p) + (size_t)w * u.cg * uvox * 8 * esz;
-          b.res = b.in0;
-          b.wo[0] = head.wo_host[w * 3], b.wo[1] = head.wo_host[w * 3 + 1], b.wo[2] = head.wo_host[w * 3 + 2];
+          const char* uw = reinterpret_cast<const char*>(u.p) + (size_t)w * u.cg * uvox * 8 * esz;
           net->last_launches++;
-          rc = launch_conv_fp32(b, bf16, false, OUT_BLEND, st);
+          if (head_tc) {
+            tc::TcIO b = io;
+            b.n = 1, b.in0 = uw, b.res = uw, b.out_kind = OUT_BLEND;
+            for (int q = 0; q < 3; ++q) b.wo[q] = head.wo_host[w * 3 + q];
+            rc = tc::tc_launch(*ru.tc, b, net->err_dev, st);
+          } else {
+            ConvArgs b = a;
+            b.n = 1, b.in0 = uw, b.res = uw;
+            for (int q = 0; q < 3; ++q) b.wo[q] = head.wo_host[w * 3 + q];
+            rc = launch_conv_fp32(b, bf16, false, OUT_BLEND, st);
+          }
           if (rc) return rc;
         }
       }
@@ -296,7 +366,10 @@ extern "C" void sgm_unet_destroy(sgm_unet* net) {
   for (auto& c : net->convs) {
     if (c.w32) cudaFree(c.w32);
     if (c.bias) cudaFree(c.bias);
+    tc::tc_free(c.tc);
+    tc::tc_free(c.tc_fused);
   }
+  if (net->err_dev) cudaFree(net->err_dev);
   delete net;
 }
 
@@ -328,6 +401,21 @@ extern "C" int32_t sgm_unet_create(const sgm_unet_desc* d, sgm_unet** out) {
     net->channels[i] = d->channels[i];
     if (i < d->n_levels) net->strides[i] = d->strides[i];
   }
+  const bool bf16 = d->precision == SGM_PRECISION_BF16;
+  if (bf16) {
+    for (int i = 0; i <= d->n_levels; ++i)
+      if (d->channels[i] % 16 != 0) {
+        set_error("precision bf16 needs channels that are multiples of 16, got %d", d->channels[i]);
+        sgm_unet_destroy(net);
+        return SGM_ERR_UNSUPPORTED;
+      }
+    if (const char* env = getenv("SGM_TC")) net->tc_mask = atoi(env);
+    if (cudaMalloc(&net->err_dev, sizeof(int)) != cudaSuccess || cudaMemset(net->err_dev, 0, sizeof(int)) != cudaSuccess) {
+      set_error("cudaMalloc(error flag) failed");
+      sgm_unet_destroy(net);
+      return SGM_ERR_CUDA;
+    }
+  }
   net->convs.resize(d->n_convs);
   for (int i = 0; i < d->n_convs; ++i) {
     const sgm_conv_desc& c = d->convs[i];
@@ -335,6 +423,11 @@ extern "C" int32_t sgm_unet_create(const sgm_unet_desc* d, sgm_unet** out) {
     pc.kind = c.kind;
     pc.cin = c.cin, pc.cout = c.cout;
     pc.cgin = ceil_div(c.cin, 8), pc.cgout = ceil_div(c.cout, 8);
+    const bool stem = (i == 0 || i == 2);  // read the planar fp32 volume, never CG8
+    if (bf16) {                            // bf16 CG8 tensors carry channels padded to 16 (even groups)
+      if (!stem) pc.cgin = ceil_div(c.cin, 16) * 2;
+      pc.cgout = ceil_div(c.cout, 16) * 2;
+    }
     pc.act = c.has_act, pc.alpha = c.alpha;
     if (c.kind == SGM_KIND_IDENTITY) continue;
     if (!(c.kernel == 1 || c.kernel == 3) || !(c.stride == 1 || c.stride == 2) || !c.weight || !c.bias) {
@@ -348,7 +441,12 @@ extern "C" int32_t sgm_unet_create(const sgm_unet_desc* d, sgm_unet** out) {
       pc.s[a] = flat ? 1 : c.stride;
       pc.pad[a] = flat ? 0 : c.kernel / 2;
     }
-    int rc = pack_fp32(c, pc, d->spatial_dims);
+    int rc = pack_fp32(c, pc, bf16);
+    if (!rc && bf16 && !stem && tc::tc_supported(c)) rc = tc::tc_pack(&c, nullptr, d->spatial_dims, &pc.tc);
+    // strided down block (levels >= 1): unit0 (index 3l) fused with its residual conv (index 3l+2)
+    if (!rc && bf16 && i >= 3 && i < 3 * d->n_levels && i % 3 == 0 && c.stride == 2 &&
+        d->convs[i + 2].kind == SGM_KIND_CONV && d->convs[i + 2].kernel == c.kernel && tc::tc_supported(c))
+      rc = tc::tc_pack(&c, &d->convs[i + 2], d->spatial_dims, &pc.tc_fused);
     if (rc) {
       sgm_unet_destroy(net);
       return rc;
@@ -501,4 +599,58 @@ extern "C" int32_t sgm_sw_finalize(const float* acc_dev, int32_t channels, const
   SGM_CUDA_CHECK(cudaGetSymbolAddress((void**)&imap_ptr, c_imap));
   const float* imaps[3] = {imap_ptr, imap_ptr + 512, imap_ptr + 1024};
   return launch_finalize(acc_dev, channels, cfg, starts_ptr, imaps, logits_dev, labels_dev, probs_dev, st);
+}
+
+extern "C" int32_t sgm_unet_check(sgm_unet* net, void* stream) {
+  SGM_REQUIRE(net, SGM_ERR_INVALID, "sgm_unet_check: null handle");
+  SGM_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+  if (!net->err_dev) return SGM_OK;
+  int flag = 0;
+  SGM_CUDA_CHECK(cudaMemcpy(&flag, net->err_dev, sizeof(int), cudaMemcpyDeviceToHost));
+  if (flag) {
+    cudaMemset(net->err_dev, 0, sizeof(int));
+    set_error("tcgen05 conv pipeline timed out (wait code %d: 1 weight ring, 2 TMEM drain, 3 weights, 4 accumulator)", flag);
+    return SGM_ERR_CUDA;
+  }
+  return SGM_OK;
+}
+
+extern "C" int32_t sgm_debug_conv(sgm_unet* net, int32_t conv_index, int32_t use_tc, int32_t fused,
+                                  const void* in0, int32_t cg0, const void* in1, int32_t cg1, const void* res,
+                                  void* out, void* out2, int32_t n, const int32_t in_dims[3], int32_t out_dims[3],
+                                  void* stream) {
+  SGM_REQUIRE(net && conv_index >= 0 && conv_index < (int)net->convs.size() && in0 && out && out_dims,
+              SGM_ERR_INVALID, "sgm_debug_conv: bad argument");
+  const PackedConv& pc = net->convs[conv_index];
+  SGM_REQUIRE(pc.kind != SGM_KIND_IDENTITY, SGM_ERR_INVALID, "sgm_debug_conv: identity layer");
+  const bool bf16 = net->precision == SGM_PRECISION_BF16;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool tr2 = pc.kind == SGM_KIND_CONV_TRANSPOSE && pc.s[1] == 2;
+  for (int i = 0; i < 3; ++i)
+    out_dims[i] = tr2 ? in_dims[i] * pc.s[i] : out_dim(in_dims[i], pc.k[i], pc.s[i], pc.pad[i]);
+  SGM_REQUIRE(cg0 + cg1 == pc.cgin, SGM_ERR_INVALID, "sgm_debug_conv: expected %d input channel groups", pc.cgin);
+  if (use_tc) {
+    const tc::TcConv* t = fused ? pc.tc_fused : pc.tc;
+    SGM_REQUIRE(bf16 && t, SGM_ERR_UNSUPPORTED, "sgm_debug_conv: no tcgen05 packing for conv %d", conv_index);
+    tc::TcIO io;
+    io.in0 = in0, io.cg0 = cg0, io.in1 = in1, io.cg1 = cg1, io.n = n;
+    for (int i = 0; i < 3; ++i) io.id[i] = in_dims[i], io.od[i] = out_dims[i];
+    io.outA = out, io.cgA = pc.cgout, io.res = res;
+    if (fused) {
+      SGM_REQUIRE(out2, SGM_ERR_INVALID, "sgm_debug_conv: fused conv needs out2");
+      io.outB = out2, io.cgB = net->convs[conv_index + 2].cgout;
+    }
+    return tc::tc_launch(*t, io, net->err_dev, st);
+  }
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.in0 = in0, a.cg0 = cg0, a.in1 = in1, a.cg1 = cg1, a.cin_real = pc.cin, a.n = n;
+  for (int i = 0; i < 3; ++i) {
+    a.id[i] = in_dims[i], a.od[i] = out_dims[i];
+    a.k[i] = pc.k[i], a.s[i] = pc.s[i], a.pad[i] = pc.pad[i];
+  }
+  a.w = pc.w32, a.bias = pc.bias, a.cout_groups = pc.cgout, a.act = pc.act, a.alpha = pc.alpha, a.c_real = pc.cout;
+  a.out = out, a.res = res;
+  if (tr2) return launch_convT_fp32(a, bf16, st);
+  return launch_conv_fp32(a, bf16, false, OUT_CG8, st);
 }

@@ -132,6 +132,11 @@ class UNetB200:
                        "sgm_unet_forward")
         return out
 
+    def check(self) -> None:
+        """Synchronise and raise if a tcgen05 pipeline reported a timeout (bf16 path)."""
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.sgm_unet_check(self._handle, _stream_ptr(self.device)), "sgm_unet_check")
+
     __call__ = forward
 
 
@@ -252,3 +257,42 @@ def sliding_window_inference(inputs: torch.Tensor, roi_size: Sequence[int], sw_b
     if return_labels or return_probs:
         return out
     return out["logits"]
+
+
+def debug_conv(net: UNetB200, conv_index: int, in0: torch.Tensor, in1: Optional[torch.Tensor] = None,
+               res: Optional[torch.Tensor] = None, *, use_tc: bool, fused: bool = False, cg_out2: int = 0):
+    """Run one convolution of the network on CG8 tensors ``[n, cg, d0, d1, d2, 8]`` (diagnostic).
+
+    Returns ``out`` (and ``out2`` for a fused strided down block).  Used by the tests to pin the
+    tcgen05 kernels against the CUDA-core kernels layer by layer.
+    """
+    lib = net._lib
+    n, cg0 = in0.shape[0], in0.shape[1]
+    dims = tuple(in0.shape[2:5])
+    od = (C.c_int32 * 3)()
+    # dry query of the output extent: run on the CUDA-core path needs the buffers, so compute here
+    specs = unet_conv_specs(net.in_channels, net.out_channels, net.channels, net.strides)
+    sp = specs[conv_index]
+    flat = net.spatial_dims == 2
+    out_dims = []
+    for a_, d_ in enumerate(dims):
+        if flat and a_ == 0:
+            out_dims.append(d_)
+        elif sp.kind == _lib.KIND_CONV_TRANSPOSE and sp.stride == 2:
+            out_dims.append(d_ * 2)
+        else:
+            out_dims.append((d_ + 2 * (sp.kernel // 2) - sp.kernel) // sp.stride + 1)
+    pad = 16 if net.precision == "bf16" else 8
+    cg_out = -(-sp.cout // pad) * (pad // 8)
+    out = torch.zeros((n, cg_out) + tuple(out_dims) + (8,), dtype=in0.dtype, device=in0.device)
+    out2 = torch.zeros((n, cg_out2) + tuple(out_dims) + (8,), dtype=in0.dtype, device=in0.device) if fused else None
+    with torch.cuda.device(net.device):
+        _lib.check(lib.sgm_debug_conv(net._handle, conv_index, int(use_tc), int(fused), in0.data_ptr(), cg0,
+                                      in1.data_ptr() if in1 is not None else None,
+                                      in1.shape[1] if in1 is not None else 0,
+                                      res.data_ptr() if res is not None else None, out.data_ptr(),
+                                      out2.data_ptr() if out2 is not None else None, n, _lib.i3(dims), od,
+                                      _stream_ptr(net.device)), "sgm_debug_conv")
+        _lib.check(lib.sgm_unet_check(net._handle, _stream_ptr(net.device)), "sgm_unet_check")
+    assert tuple(od) == tuple(out_dims), (tuple(od), out_dims)
+    return (out, out2) if fused else out

@@ -1,0 +1,87 @@
+"""Layer-by-layer diagnostic: tcgen05 conv kernels vs the CUDA-core kernels on identical bf16 CG8
+inputs (run on the GPU box: `python tests/diag_tc_layers.py`).  Prints one line per case."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from segmantic_b200.seg import engine  # noqa: E402
+from segmantic_b200.synthetic import synthetic_state_dict  # noqa: E402
+
+
+def cg8(n, cg, dims, seed, dev, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    t = torch.randn((n, cg) + tuple(dims) + (8,), generator=g) * scale
+    return t.to(torch.bfloat16).to(dev)
+
+
+def run_case(net, name, idx, in0, in1=None, res=None, fused=False, cg_out2=0):
+    try:
+        ref = engine.debug_conv(net, idx, in0, in1, res, use_tc=False)
+        if fused:
+            ref2 = engine.debug_conv(net, idx + 2, in0, None, None, use_tc=False)
+            out, out2 = engine.debug_conv(net, idx, in0, in1, res, use_tc=True, fused=True, cg_out2=cg_out2)
+            pairs = [("main", ref, out), ("resid", ref2, out2)]
+        else:
+            out = engine.debug_conv(net, idx, in0, in1, res, use_tc=True)
+            pairs = [("out", ref, out)]
+        ok = True
+        for tag, r, o in pairs:
+            r32, o32 = r.float(), o.float()
+            scale = float(r32.abs().max())
+            err = float((r32 - o32).abs().max())
+            nbad = int(((r32 - o32).abs() > 2e-2 * max(scale, 1e-6)).sum())
+            good = err <= 2e-2 * max(scale, 1e-6)
+            ok &= good
+            msg = f"{name:34s} {tag:5s} shape={tuple(o.shape)} max|ref|={scale:.4g} maxerr={err:.4g} bad={nbad}/{o.numel()}"
+            if not good:
+                bad = ((r32 - o32).abs() > 2e-2 * max(scale, 1e-6)).nonzero()
+                msg += f" firstbad={bad[0].tolist()} ref={float(r32[tuple(bad[0])]):.4g} got={float(o32[tuple(bad[0])]):.4g}"
+                msg += f" lastbad={bad[-1].tolist()} nz_out={int((o32 != 0).sum())}"
+            print(("PASS " if good else "FAIL ") + msg, flush=True)
+        return ok
+    except Exception as e:  # noqa: BLE001
+        print(f"ERROR {name}: {type(e).__name__}: {e}", flush=True)
+        return False
+
+
+def main():
+    dev = torch.device("cuda:0")
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    sd = synthetic_state_dict(3, 1, 10, seed=0)
+    net = engine.UNetB200(sd, spatial_dims=3, in_channels=1, out_channels=10, device=dev, precision="bf16")
+    results = []
+    if which in ("all", "s1"):
+        # stride-1 3x3x3 convs (indices: d0.unit1=1, d1.unit1=4, d2.unit1=7, d3.unit1=10, bottom 12/13, bottom k1 res=14,
+        # up ru: 16, 18, 20, head 22)
+        results.append(run_case(net, "s1 16->16 d0.unit1 (tiny 8^3)", 1, cg8(1, 2, (8, 8, 8), 1, dev)))
+        results.append(run_case(net, "s1 16->16 d0.unit1 24x20x40 n2 +res", 1, cg8(2, 2, (24, 20, 40), 2, dev),
+                                res=cg8(2, 2, (24, 20, 40), 3, dev)))
+        results.append(run_case(net, "s1 32->32 d1.unit1 24^3", 4, cg8(1, 4, (24, 24, 24), 4, dev)))
+        results.append(run_case(net, "s1 64->64 d2.unit1 12^3", 7, cg8(2, 8, (12, 12, 12), 5, dev)))
+        results.append(run_case(net, "s1 128->128 d3.unit1 6^3", 10, cg8(2, 16, (6, 6, 6), 6, dev)))
+        results.append(run_case(net, "s1 128->256 bottom.unit0 6^3", 12, cg8(1, 16, (6, 6, 6), 7, dev)))
+        results.append(run_case(net, "s1 256->256 bottom.unit1 6^3", 13, cg8(1, 32, (6, 6, 6), 8, dev)))
+        results.append(run_case(net, "k1 128->256 bottom.residual 6^3", 14, cg8(1, 16, (6, 6, 6), 9, dev)))
+        results.append(run_case(net, "s1 10->10 head conv 32^3", 22, cg8(1, 2, (32, 32, 32), 10, dev)))
+    if which in ("all", "s2"):
+        results.append(run_case(net, "s2 16->32(+32) d1.unit0 fused 16^3", 3, cg8(1, 2, (16, 16, 16), 11, dev),
+                                fused=True, cg_out2=4))
+        results.append(run_case(net, "s2 16->32(+32) d1 fused 48x32x24 n2", 3, cg8(2, 2, (48, 32, 24), 12, dev),
+                                fused=True, cg_out2=4))
+        results.append(run_case(net, "s2 32->64(+64) d2.unit0 fused 24^3", 6, cg8(1, 4, (24, 24, 24), 13, dev),
+                                fused=True, cg_out2=8))
+        results.append(run_case(net, "s2 64->128(+128) d3 fused 12^3", 9, cg8(1, 8, (12, 12, 12), 14, dev),
+                                fused=True, cg_out2=16))
+        results.append(run_case(net, "s2 16->32 d1.unit0 alone 16^3", 3, cg8(1, 2, (16, 16, 16), 15, dev)))
+    if which in ("all", "t2"):
+        results.append(run_case(net, "t2 384->64 up3 6^3", 15, cg8(1, 16, (6, 6, 6), 16, dev), cg8(1, 32, (6, 6, 6), 17, dev)))
+        results.append(run_case(net, "t2 128->32 up2 12^3", 17, cg8(1, 8, (12, 12, 12), 18, dev), cg8(1, 8, (12, 12, 12), 19, dev)))
+        results.append(run_case(net, "t2 64->16 up1 24x16x20 n2", 19, cg8(2, 4, (24, 16, 20), 20, dev), cg8(2, 4, (24, 16, 20), 21, dev)))
+        results.append(run_case(net, "t2 32->10 up0 16^3", 21, cg8(1, 2, (16, 16, 16), 22, dev), cg8(1, 2, (16, 16, 16), 23, dev)))
+    print(f"SUMMARY {sum(results)}/{len(results)} passed", flush=True)
+
+
+if __name__ == "__main__":
+    main()
