@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""Benchmark of segmantic's volumetric prediction hot path on B200 (driver contract: one JSON line).
+
+Workload (BASELINE.json configs[1], the configuration `metric` is quoted on): MONAI UNet 3D
+(channels 16-32-64-128-256, strides 2, 1 input channel, 10 tissues) over a synthetic 256^3 CT-like
+volume, roi 96^3, overlap 0.5, Gaussian blend, bf16, argmax label map.  A "step" = one full
+sliding-window prediction of the volume: 125 windows through the network, importance-weighted overlap
+accumulation, normalise + argmax.  (No resampling stage in this config: spacing is already 1 mm.)
+
+  value   Mvoxel/s with the (normalised) volume resident in HBM when the timed region starts.
+  e2e     the same through the public API `segmantic_b200.seg.monai_unet.predict_volume` with HOST
+          buffers: pinned H2D of the raw volume, z-score normalisation, foreground crop, prediction,
+          D2H of the uint8 label map -- all inside the timed region.
+  N > 1   weak scaling: the volume grows to (256*N) x 256 x 256, axis 0 is cut into N output slabs with
+          ROI halos, every rank predicts its slab (bit-identical to the single-GPU result) and the uint8
+          label slabs are gathered over NCCL to rank 0; time = max over ranks.
+
+`--impl reference` times the CPU restatement of the reference path (oracle/; the reference's own
+MONAI/SimpleITK stack is not installable here) on the host cores for the same workload, on a bounded
+sample of windows, extrapolated linearly and stated in `cpu_baseline.sample`.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+VOL = (256, 256, 256)
+ROI = (96, 96, 96)
+CLASSES = 10
+OVERLAP = 0.5
+MODE = "gaussian"
+METRIC = "3D UNet sliding-window predict throughput"
+UNIT = "Mvoxel/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=float(d["hbm_gbs"]), bf16=float(d["bf16_tflops"]),
+                    bf16_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), source="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception as e:  # noqa: BLE001
+            log("clock sampler unavailable:", e)
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["unavailable"])
+        time.sleep(0.12)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])), mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def conv_flops(spec, roi, level_dims):
+    """Algorithmic FLOPs (2*MAC, no channel padding) of one conv for one window."""
+    k = spec.kernel ** 3
+    return 2.0 * spec.cin * spec.cout * k * level_dims
+
+
+def per_window_layer_flops(specs, roi):
+    """{conv index: algorithmic FLOP per window}.  conv: 2*Cin*Cout*k^3*V_out; transposed: ...*V_in."""
+    from segmantic_b200.seg.unet_spec import KIND_CONV_TRANSPOSE, KIND_IDENTITY
+    n = (len(specs) - 3) // 5
+    vox = [float(np.prod(roi))]
+    for i in range(n):
+        vox.append(vox[-1] / 8.0)
+    out = {}
+    idx = 0
+    for i in range(n):
+        for j in range(3):
+            sp = specs[idx]
+            if sp.kind != KIND_IDENTITY:
+                out[idx] = 2.0 * sp.cin * sp.cout * sp.kernel ** 3 * vox[i + 1]
+            idx += 1
+    for j in range(3):
+        sp = specs[idx]
+        if sp.kind != KIND_IDENTITY:
+            out[idx] = 2.0 * sp.cin * sp.cout * sp.kernel ** 3 * vox[n]
+        idx += 1
+    for i in range(n - 1, -1, -1):
+        sp = specs[idx]
+        out[idx] = 2.0 * sp.cin * sp.cout * 27 * vox[i + 1] if sp.kind == KIND_CONV_TRANSPOSE else 0.0
+        idx += 1
+        sp = specs[idx]
+        out[idx] = 2.0 * sp.cin * sp.cout * 27 * vox[i]
+        idx += 1
+    return out
+
+
+def make_block(seed=1):
+    """The 256^3 normalised CT-like block (float32 [1, X, Y, Z]) + its raw version."""
+    from segmantic_b200.synthetic import synthetic_volume
+    raw = synthetic_volume(VOL, seed=seed)
+    norm = (raw - raw.mean()) / raw.std(unbiased=False)
+    return raw, norm
+
+
+# ---------------------------------------------------------------------------------------- CPU arm
+def cpu_sample(n_windows: int, threads: int, seed=1):
+    """Times the oracle on `n_windows` of the workload's 125 windows (+ their blend) and extrapolates."""
+    from oracle import sliding_window as osw
+    from oracle.unet import UNet, load_checkpoint_into
+    from segmantic_b200.synthetic import synthetic_state_dict
+    torch.set_num_threads(threads)
+    sd = synthetic_state_dict(3, 1, CLASSES, seed=0)
+    net = UNet(3, 1, CLASSES)
+    load_checkpoint_into(net, sd)
+    net.eval()
+    starts = osw.window_starts(VOL, ROI, OVERLAP)
+    g = torch.Generator().manual_seed(seed)
+    # a strip of the volume holding n_windows consecutive (50 % overlapping) windows
+    vol = torch.randn((1, 1, ROI[0], ROI[1], ROI[2] + 48 * (n_windows - 1)), generator=g)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        out = osw.sliding_window_inference(vol, ROI, 4, net, overlap=OVERLAP, mode=MODE)
+        out.argmax(1)
+    dt = time.perf_counter() - t0
+    nwin_done = len(osw.window_starts(vol.shape[2:], ROI, OVERLAP))
+    total_windows = len(starts)
+    est = dt * total_windows / nwin_done
+    return dict(seconds_sample=dt, windows_sample=nwin_done, windows_total=total_windows,
+                seconds_extrapolated=est, mvox_s=float(np.prod(VOL)) / est / 1e6)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    vals = []
+    for i in range(max(1, args.warmup) + args.steps):
+        r = cpu_sample(args.cpu_windows, threads)
+        if i >= max(1, args.warmup):
+            vals.append(r)
+        log(f"[reference] step {i}: {r['seconds_sample']:.2f} s for {r['windows_sample']} windows "
+            f"-> {r['mvox_s']:.4f} Mvoxel/s extrapolated")
+    v = float(np.mean([r["mvox_s"] for r in vals]))
+    ms = float(np.mean([r["seconds_extrapolated"] for r in vals])) * 1e3
+    sample = (f"{vals[0]['windows_sample']} of {vals[0]['windows_total']} ROI windows (96^3, 10 classes) through the "
+              f"torch-CPU oracle UNet + Gaussian blend + argmax, extrapolated linearly to the 256^3 volume")
+    line = dict(impl="reference", metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic",
+                config=dict(workload="configs[1]: UNet3D 10 tissues, 256^3, roi 96^3, overlap 0.5, gaussian",
+                            impl="oracle port of the reference path (torch CPU fp32); MONAI/SimpleITK not installable"),
+                cpu_baseline=dict(value=v, unit=UNIT, cores=threads, kind="port", sample=sample),
+                e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------- GPU arm
+def run_b200(args):
+    import torch.distributed as dist
+    from segmantic_b200.seg import engine
+    from segmantic_b200.seg.monai_unet import Net, predict_volume
+    from segmantic_b200.seg.sliding_window import make_schedule, slab_partition
+    from segmantic_b200.seg.unet_spec import unet_conv_specs
+    from segmantic_b200.synthetic import synthetic_state_dict
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback in segmantic_b200)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pk = peaks()
+    sd = synthetic_state_dict(3, 1, CLASSES, seed=0)
+    net = engine.UNetB200(sd, spatial_dims=3, in_channels=1, out_channels=CLASSES, device=dev,
+                          precision=args.precision)
+    raw, norm = make_block(seed=1)
+    gshape = (VOL[0] * world, VOL[1], VOL[2])
+    sched = make_schedule(gshape, ROI, OVERLAP, MODE)
+    if world > 1:
+        part = slab_partition(sched, world)[rank]
+        # the global volume is the 256^3 block tiled along axis 0; a rank uploads only its halo'ed slab
+        idx = torch.arange(part["vol_x0"], part["vol_x1"]) % VOL[0]
+        vol_dev = norm[:, idx].contiguous().to(dev)
+    else:
+        part = None
+        vol_dev = norm.to(dev)
+    n_win = (len(sched.starts[0]) if part is None else part["a0_end"] - part["a0_begin"]) * \
+        len(sched.starts[1]) * len(sched.starts[2])
+    log(f"[rank {rank}] volume {gshape}, {n_win} windows on this rank, precision {args.precision}, "
+        f"sw_batch {args.sw_batch}")
+
+    def step():
+        if part is None:
+            res = engine.sliding_window_inference(vol_dev[None], ROI, args.sw_batch, net, overlap=OVERLAP, mode=MODE,
+                                                  return_labels=True, return_logits=False)
+            return res["labels"]
+        res = engine.sliding_window_inference_slab(vol_dev, gshape, part, ROI, args.sw_batch, net, overlap=OVERLAP,
+                                                   mode=MODE)
+        lab = res["labels"]  # [nx, Y, Z] uint8 for planes [x0, x1)
+        # gather label slabs on rank 0 (NCCL over NVLink); slabs have unequal heights -> pad to the max
+        maxh = max(p["x1"] - p["x0"] for p in slab_partition(sched, world))
+        buf = torch.zeros((maxh,) + lab.shape[1:], dtype=torch.uint8, device=dev)
+        buf[: lab.shape[0]] = lab
+        outs = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
+        dist.gather(buf, outs, dst=0)
+        return outs
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    net.check()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    net.set_profiling(not args.no_profile)
+    net.get_profile()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        out = step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    launches_step = net.last_launch_count + 1  # + the normalise/argmax kernel
+    prof = net.get_profile()
+    net.set_profiling(False)
+    clocks = sampler.stop() if rank == 0 else None
+    net.check()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    total_vox = float(np.prod(gshape))
+    value = total_vox / (ms * 1e-3) / 1e6
+
+    # ---- end to end through the public API with host buffers (rank-local slab semantics for N > 1 are
+    # the same compute; the e2e number is reported for the single-volume API call on every rank)
+    e2e = None
+    if True:
+        pnet = Net(num_classes=CLASSES, num_channels=1, spatial_dims=3)
+        pnet.load_state_dict(sd)
+        pnet.to(dev)
+        host = raw.clone().pin_memory()
+        kw = dict(overlap=OVERLAP, mode=MODE, sw_batch_size=args.sw_batch, precision=args.precision)
+        for _ in range(2):
+            predict_volume(pnet, host, None, (), **kw)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps = max(1, min(args.steps, 5))
+        for _ in range(e2e_steps):
+            lab = predict_volume(pnet, host, None, (), **kw)  # returns a HOST uint8 label map
+        torch.cuda.synchronize(dev)
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+        e2e = dict(value=float(np.prod(VOL)) * world / (e2e_ms * 1e-3) / 1e6, unit=UNIT,
+                   h2d_bytes_per_step=int(host.numel() * 4), d2h_bytes_per_step=int(lab.numel()),
+                   ms_per_step=e2e_ms,
+                   note="predict_volume(host fp32 volume) -> host uint8 labels; N>1: one 256^3 volume per rank")
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (the head: conv C->C + residual + weighted blend accumulate)
+    specs = unet_conv_specs(1, CLASSES)
+    flops = per_window_layer_flops(specs, ROI)
+    layers = []
+    tot_ms = sum(p[1] for p in prof) or 1.0
+    for i, (role, pms, cnt) in enumerate(prof):
+        if cnt == 0:
+            continue
+        fl = flops.get(i, 0.0)
+        wins = n_win * args.steps
+        tf = fl * wins / (pms * 1e-3) / 1e12 if pms > 0 else 0.0
+        layers.append(dict(conv=role, ms_per_step=pms / args.steps, launches_per_step=cnt // args.steps,
+                           share=pms / tot_ms, gflop_per_window=fl / 1e9, tflops=tf,
+                           frac_bf16_peak=tf / pk["bf16_sustained"]))
+    head = prof[-1]
+    roi_vox = float(np.prod(ROI))
+    # algorithmic bytes per head launch (one window): read u (C ch bf16; the residual is the same
+    # tensor) + read-modify-write of the fp32 accumulator for C classes  = (2C + 8C) * roi^3
+    esz = 2 if args.precision == "bf16" else 4
+    head_bytes = (esz * CLASSES + 8 * CLASSES) * roi_vox
+    roofline = None
+    if head[2] > 0 and head[1] > 0:
+        per_launch_s = head[1] * 1e-3 / head[2]
+        ach = head_bytes / per_launch_s / 1e9
+        roofline = dict(kernel="tc_conv_kernel[head: conv CxC + residual + importance-weighted accumulate]",
+                        bound="hbm", achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"], traffic=None,
+                        peak_source=pk["source"], us_per_launch=per_launch_s * 1e6,
+                        algorithmic_bytes_per_launch=head_bytes,
+                        tflops=flops[len(specs) - 1] / per_launch_s / 1e12,
+                        frac_bf16_peak=flops[len(specs) - 1] / per_launch_s / 1e12 / pk["bf16_sustained"])
+    conv_ms = sum(l["ms_per_step"] for l in layers)
+    conv_tf = sum(flops.get(i, 0.0) for i in range(len(specs))) * n_win / (conv_ms * 1e-3) / 1e12 if conv_ms else 0.0
+
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        r = cpu_sample(args.cpu_windows, threads)
+        cpu = dict(value=r["mvox_s"], unit=UNIT, cores=threads, kind="port",
+                   sample=f"{r['windows_sample']} of {r['windows_total']} windows ({r['seconds_sample']:.1f} s) through "
+                          f"the torch-CPU oracle UNet + blend + argmax, extrapolated linearly")
+
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
+                ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype=args.precision, data="synthetic",
+                config=dict(workload="configs[1]: MONAI UNet3D (16-32-64-128-256, strides 2, 1 ch, 10 tissues), "
+                                     f"synthetic {gshape[0]}x{gshape[1]}x{gshape[2]} volume, roi 96^3, overlap 0.5, "
+                                     "gaussian blend, argmax labels",
+                            windows=int(n_win if world == 1 else sched.n_windows), sw_batch=args.sw_batch,
+                            parallelism=f"slab{world}" if world > 1 else "single",
+                            l2="no flush: per-step working set (67 MB volume + 671 MB accumulator + activations) "
+                               "exceeds the 126 MB L2"),
+                e2e=e2e, gpu_launches=int(launches_step * args.steps), clocks=clocks, roofline=roofline,
+                cpu_baseline=cpu,
+                conv_stack=dict(ms_per_step=conv_ms, tflops=conv_tf, frac_bf16_peak=conv_tf / pk["bf16_sustained"],
+                                peak_tflops=pk["bf16_sustained"], layers=layers))
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--sw-batch", type=int, default=4)
+    ap.add_argument("--cpu-windows", type=int, default=32, help="windows in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -126,6 +126,11 @@ SGM_API int32_t sgm_debug_conv(sgm_unet* net, int32_t conv_index, int32_t use_tc
                                const void* in0, int32_t cg0, const void* in1, int32_t cg1, const void* res,
                                void* out, void* out2, int32_t n, const int32_t in_dims[3],
                                int32_t out_dims[3], void* stream);
+/* Per-convolution device timing: while on, every conv launch is bracketed by a CUDA-event pair on the
+ * launching stream.  sgm_unet_get_profile synchronises, returns the accumulated milliseconds and launch
+ * counts per convolution (canonical order, n = n_convs) and resets the counters. */
+SGM_API int32_t sgm_unet_set_profiling(sgm_unet* net, int32_t on);
+SGM_API int32_t sgm_unet_get_profile(sgm_unet* net, double* ms, int64_t* launches, int32_t n, void* stream);
 /* Number of kernel launches the last forward / sw_accumulate on this handle enqueued. */
 SGM_API int64_t sgm_unet_last_launch_count(const sgm_unet* net);
 

@@ -63,6 +63,9 @@ SIGNATURES = {
                                      C.c_int64, C.c_void_p]),
     "sgm_unet_last_launch_count": (C.c_int64, [C.c_void_p]),
     "sgm_unet_check": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "sgm_unet_set_profiling": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "sgm_unet_get_profile": (C.c_int32, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32,
+                                         C.c_void_p]),
     "sgm_debug_conv": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                    C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, _I3,
                                    _I3, C.c_void_p]),

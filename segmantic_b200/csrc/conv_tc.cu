@@ -24,6 +24,7 @@
 #include "conv_tc.cuh"
 
 #include <algorithm>
+#include <stdlib.h>
 #include <string.h>
 
 namespace sgm {
@@ -33,7 +34,7 @@ namespace {
 
 constexpr int kThreads = 192;
 constexpr int kSmemBudget = 110 * 1024;   // two CTAs per SM
-constexpr long long kWaitCycles = 4000000000LL;
+constexpr long long kWaitCycles = 1000000000LL;
 
 struct KArgs {
   const __nv_bfloat16* in0;
@@ -453,7 +454,6 @@ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 bool tc_supported(const sgm_conv_desc& d) {
   if (d.kind == SGM_KIND_IDENTITY) return false;
-  if (d.cin < 16 && d.cin % 8 != 0) return false;  // the 1..8-channel stem stays on CUDA cores
   return (d.kernel == 3 || d.kernel == 1) && (d.stride == 1 || d.stride == 2);
 }
 
@@ -713,7 +713,8 @@ int tc_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t
         const double mma = (double)ntl * nblk * (32.0 + N / 4.0);
         const double load = (double)a.nslab * c.cgin * P * 16 / 24.0;
         const double epi = (double)ntl * c.ncls * (N / 16) * 60.0;
-        const double cta = std::max(mma, epi) + load + 4000.0;
+        const double wload = (double)nblk * N * 32 / 40.0;  // every CTA streams the whole filter bank from L2
+        const double cta = std::max(std::max(mma, epi), wload) + load + 4000.0;
         const double waves = (double)((nct + 295) / 296);
         const double cost = waves * cta;
         if (cost < best) best = cost, bt[0] = t[0], bt[1] = t[1], bt[2] = t[2];
@@ -751,6 +752,15 @@ int tc_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t
   a.c_real = c.c_real;
   a.error_flag = error_flag_dev;
 
+  static const bool dbg = getenv("SGM_DEBUG") != nullptr;
+  if (dbg)
+    fprintf(stderr,
+            "[tc_launch] mode=%d N=%d nblk=%d ncls=%d cgin=%d rd=(%d,%d,%d) t=(%d,%d,%d) H=(%d,%d,%d) P=%d nslab=%d "
+            "row_first=%d ntiles=%d tpc=%d nchunks=%d nbuf=%d cols/buf=%d tmem=%d G=%d ngroups=%d nstages=%d res=%d "
+            "a_units=%d smem=%d grid=(%d,%d,%d)\n",
+            a.mode, N, nblk, a.ncls, a.cgin, a.rd[0], a.rd[1], a.rd[2], a.t[0], a.t[1], a.t[2], a.H[0], a.H[1], a.H[2],
+            a.P, a.nslab, a.row_first, a.ntiles, a.tpc, a.nchunks, a.nbuf, a.cols_per_buf, a.tmem_cols, a.G, a.ngroups,
+            a.nstages, a.resident, a.a_units, smem_bytes, a.nt[0] * a.nt[1] * a.nt[2], c.ncoblk, io.n);
   static bool attr_set = false;
   if (!attr_set) {
     SGM_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));

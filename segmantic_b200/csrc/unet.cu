@@ -49,6 +49,26 @@ struct sgm_unet {
   // with the residual branch), 4 transposed convs, 8 head (conv + blend epilogue)
   int tc_mask = 15;
   int* err_dev = nullptr;  // device flag raised by a tcgen05 pipeline timeout
+  // optional per-convolution CUDA-event timing (sgm_unet_set_profiling)
+  struct ProfEv {
+    cudaEvent_t a, b;
+    int conv;
+  };
+  bool profiling = false;
+  std::vector<ProfEv> prof_pending;
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<double> prof_ms;
+  std::vector<int64_t> prof_n;
+  cudaEvent_t ev_get() {
+    cudaEvent_t e = nullptr;
+    if (!ev_pool.empty()) {
+      e = ev_pool.back();
+      ev_pool.pop_back();
+    } else {
+      cudaEventCreate(&e);
+    }
+    return e;
+  }
 };
 
 namespace sgm {
@@ -134,6 +154,22 @@ int run_network(sgm_unet* net, const float* vol, long long vol_cstride, int vd1,
   const int L = net->n_levels;
   const size_t esz = net->precision == SGM_PRECISION_BF16 ? 2 : 4;
   const bool bf16 = net->precision == SGM_PRECISION_BF16;
+  struct Prof {  // records a CUDA-event pair around one launch when profiling is on
+    sgm_unet* net;
+    cudaStream_t st;
+    cudaEvent_t b = nullptr;
+    Prof(sgm_unet* n, cudaStream_t s, const PackedConv* pc, bool dry) : net(n), st(s) {
+      if (dry || !n->profiling) return;
+      sgm_unet::ProfEv e;
+      e.a = n->ev_get(), e.b = n->ev_get(), e.conv = (int)(pc - n->convs.data());
+      cudaEventRecord(e.a, s);
+      b = e.b;
+      n->prof_pending.push_back(e);
+    }
+    ~Prof() {
+      if (b) cudaEventRecord(b, st);
+    }
+  };
   auto alloc = [&](int cg, const int d[3]) {
     Tensor t;
     t.cg = cg;
@@ -184,6 +220,7 @@ int run_network(sgm_unet* net, const float* vol, long long vol_cstride, int vd1,
     if (dry) return SGM_OK;
     SGM_REQUIRE(in0.cg + (in1 ? in1->cg : 0) == pc.cgin, SGM_ERR_INVALID, "channel-group mismatch");
     net->last_launches++;
+    Prof prof(net, st, &pc, dry);
     if (bf16 && (net->tc_mask & tc_bit(pc))) {
       tc::TcIO io = tc_io(in0, in1, od);
       io.outA = out.p, io.cgA = out.cg, io.res = res ? res->p : nullptr;
@@ -204,6 +241,7 @@ int run_network(sgm_unet* net, const float* vol, long long vol_cstride, int vd1,
       r = alloc(rs.cgout, od);
       if (dry) return SGM_OK;
       net->last_launches++;
+      Prof prof(net, st, &u0, dry);
       tc::TcIO io = tc_io(in0, nullptr, od);
       io.outA = t.p, io.cgA = t.cg, io.outB = r.p, io.cgB = r.cg;
       return tc::tc_launch(*u0.tc_fused, io, net->err_dev, st);
@@ -248,6 +286,7 @@ int run_network(sgm_unet* net, const float* vol, long long vol_cstride, int vd1,
           a.out = which ? r.p : t.p;
           a.vol_cstride = vol_cstride, a.vd1 = vd1, a.vd2 = vd2, a.win_origin = win_origin_dev;
           net->last_launches++;
+          Prof prof(net, st, &pc, dry);
           int rc = launch_conv_fp32(a, bf16, true, OUT_CG8, st);
           if (rc) return rc;
         }
@@ -315,6 +354,7 @@ int run_network(sgm_unet* net, const float* vol, long long vol_cstride, int vd1,
       io.imap_floor = head.floor;
       if (head.kind == OUT_PLANAR) {
         net->last_launches++;
+        Prof prof(net, st, &ru, dry);
         if (head_tc) {
           io.res = u.p, io.out_kind = OUT_PLANAR;
           rc = tc::tc_launch(*ru.tc, io, net->err_dev, st);
@@ -327,6 +367,7 @@ int run_network(sgm_unet* net, const float* vol, long long vol_cstride, int vd1,
         for (int w = 0; w < n; ++w) {  // one launch per window: plain RMW, MONAI's window order
           const char* uw = reinterpret_cast<const char*>(u.p) + (size_t)w * u.cg * uvox * 8 * esz;
           net->last_launches++;
+          Prof prof(net, st, &ru, dry);
           if (head_tc) {
             tc::TcIO b = io;
             b.n = 1, b.in0 = uw, b.res = uw, b.out_kind = OUT_BLEND;
@@ -370,6 +411,8 @@ extern "C" void sgm_unet_destroy(sgm_unet* net) {
     tc::tc_free(c.tc_fused);
   }
   if (net->err_dev) cudaFree(net->err_dev);
+  for (auto& e : net->prof_pending) cudaEventDestroy(e.a), cudaEventDestroy(e.b);
+  for (auto& e : net->ev_pool) cudaEventDestroy(e);
   delete net;
 }
 
@@ -653,4 +696,33 @@ extern "C" int32_t sgm_debug_conv(sgm_unet* net, int32_t conv_index, int32_t use
   a.out = out, a.res = res;
   if (tr2) return launch_convT_fp32(a, bf16, st);
   return launch_conv_fp32(a, bf16, false, OUT_CG8, st);
+}
+
+extern "C" int32_t sgm_unet_set_profiling(sgm_unet* net, int32_t on) {
+  SGM_REQUIRE(net, SGM_ERR_INVALID, "sgm_unet_set_profiling: null handle");
+  net->profiling = on != 0;
+  return SGM_OK;
+}
+
+extern "C" int32_t sgm_unet_get_profile(sgm_unet* net, double* ms, int64_t* launches, int32_t n, void* stream) {
+  SGM_REQUIRE(net && ms && launches && n == (int)net->convs.size(), SGM_ERR_INVALID,
+              "sgm_unet_get_profile: expected arrays of %d entries", net ? (int)net->convs.size() : 0);
+  SGM_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+  net->prof_ms.resize(n, 0.0);
+  net->prof_n.resize(n, 0);
+  for (auto& e : net->prof_pending) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, e.a, e.b) == cudaSuccess) {
+      net->prof_ms[e.conv] += t;
+      net->prof_n[e.conv] += 1;
+    }
+    net->ev_pool.push_back(e.a);
+    net->ev_pool.push_back(e.b);
+  }
+  net->prof_pending.clear();
+  for (int i = 0; i < n; ++i) {
+    ms[i] = net->prof_ms[i], launches[i] = net->prof_n[i];
+    net->prof_ms[i] = 0.0, net->prof_n[i] = 0;
+  }
+  return SGM_OK;
 }

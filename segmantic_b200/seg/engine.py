@@ -139,6 +139,20 @@ class UNetB200:
 
     __call__ = forward
 
+    def set_profiling(self, on: bool) -> None:
+        _lib.check(self._lib.sgm_unet_set_profiling(self._handle, int(bool(on))), "sgm_unet_set_profiling")
+
+    def get_profile(self):
+        """[(role, ms, launches)] per convolution since the last call (device time, CUDA events)."""
+        specs = unet_conv_specs(self.in_channels, self.out_channels, self.channels, self.strides)
+        n = len(specs)
+        ms = (C.c_double * n)()
+        cnt = (C.c_int64 * n)()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.sgm_unet_get_profile(self._handle, ms, cnt, n, _stream_ptr(self.device)),
+                       "sgm_unet_get_profile")
+        return [(specs[i].role, float(ms[i]), int(cnt[i])) for i in range(n)]
+
 
 def _make_cfg(sched: Schedule, sw_batch: int, a0=None, vol=None, acc=None):
     cfg = _lib.SwCfg()
@@ -161,6 +175,35 @@ def _make_cfg(sched: Schedule, sw_batch: int, a0=None, vol=None, acc=None):
     cfg.vol_x0, cfg.vol_nx = vol if vol is not None else (0, sched.padded_size[0])
     cfg.acc_x0, cfg.acc_nx = acc if acc is not None else (0, sched.padded_size[0])
     return cfg, keep
+
+
+def _sw_run(net: UNetB200, vol: torch.Tensor, sched: Schedule, sw_batch_size: int, a0, vol_rng, acc_rng,
+            return_logits: bool, return_labels: bool, return_probs: bool):
+    """Accumulate + finalise planes ``acc_rng`` from ``vol`` = planes ``vol_rng`` of the padded volume.
+    Returns ``(logits, labels, probs)`` device tensors (or None) of shape ``[C|-, nx, Y, Z]``."""
+    lib = net._lib
+    C_out = net.out_channels
+    x0, nx = acc_rng
+    plane = (sched.padded_size[1], sched.padded_size[2])
+    cfg, keep = _make_cfg(sched, sw_batch_size, a0, vol_rng, (x0, nx))
+    acc = torch.zeros((C_out, nx) + plane, dtype=torch.float32, device=net.device)
+    with torch.cuda.device(net.device):
+        st = _stream_ptr(net.device)
+        need = lib.sgm_sw_workspace_bytes(net._handle, C.byref(cfg))
+        _lib.check(need, "sgm_sw_workspace_bytes")
+        ws = net._workspace(need)
+        _lib.check(lib.sgm_sw_accumulate(net._handle, vol.data_ptr(), C.byref(cfg), acc.data_ptr(),
+                                         ws.data_ptr(), ws.numel(), st), "sgm_sw_accumulate")
+        logits = torch.empty_like(acc) if return_logits else None
+        labels = torch.empty((nx,) + plane, dtype=torch.uint8, device=net.device) if return_labels else None
+        probs = torch.empty_like(acc) if return_probs else None
+        _lib.check(lib.sgm_sw_finalize(acc.data_ptr(), C_out, C.byref(cfg),
+                                       logits.data_ptr() if logits is not None else None,
+                                       labels.data_ptr() if labels is not None else None,
+                                       probs.data_ptr() if probs is not None else None, st),
+                   "sgm_sw_finalize")
+    del keep
+    return logits, labels, probs
 
 
 def sliding_window_inference(inputs: torch.Tensor, roi_size: Sequence[int], sw_batch_size: int,
@@ -192,7 +235,6 @@ def sliding_window_inference(inputs: torch.Tensor, roi_size: Sequence[int], sw_b
             pad += [lo, sched.padded_size[a] - size3[a] - lo]
         vol = torch.nn.functional.pad(vol, pad, mode="constant", value=0.0)
     vol = vol.contiguous()
-    lib = net._lib
     C_out = net.out_channels
     if slab is None:
         x0, x1 = 0, sched.padded_size[0]
@@ -215,24 +257,8 @@ def sliding_window_inference(inputs: torch.Tensor, roi_size: Sequence[int], sw_b
         if return_probs:
             out["probs"] = torch.empty((1, C_out) + empty, device=net.device)
         return out if (return_labels or return_probs) else out["logits"]
-    cfg, keep = _make_cfg(sched, sw_batch_size, a0, vol_rng, (x0, nx))
-    acc = torch.zeros((C_out, nx) + plane, dtype=torch.float32, device=net.device)
-    with torch.cuda.device(net.device):
-        st = _stream_ptr(net.device)
-        need = lib.sgm_sw_workspace_bytes(net._handle, C.byref(cfg))
-        _lib.check(need, "sgm_sw_workspace_bytes")
-        ws = net._workspace(need)
-        _lib.check(lib.sgm_sw_accumulate(net._handle, vol.data_ptr(), C.byref(cfg), acc.data_ptr(),
-                                         ws.data_ptr(), ws.numel(), st), "sgm_sw_accumulate")
-        logits = torch.empty_like(acc) if return_logits else None
-        labels = torch.empty((nx,) + plane, dtype=torch.uint8, device=net.device) if return_labels else None
-        probs = torch.empty_like(acc) if return_probs else None
-        _lib.check(lib.sgm_sw_finalize(acc.data_ptr(), C_out, C.byref(cfg),
-                                       logits.data_ptr() if logits is not None else None,
-                                       labels.data_ptr() if labels is not None else None,
-                                       probs.data_ptr() if probs is not None else None, st),
-                   "sgm_sw_finalize")
-    del keep
+    logits, labels, probs = _sw_run(net, vol, sched, sw_batch_size, a0, vol_rng, (x0, nx), return_logits,
+                                    return_labels, return_probs)
 
     def crop(t, lead):
         # undo the roi padding (axes 1, 2 always; axis 0 only without a slab)
@@ -257,6 +283,32 @@ def sliding_window_inference(inputs: torch.Tensor, roi_size: Sequence[int], sw_b
     if return_labels or return_probs:
         return out
     return out["logits"]
+
+
+def sliding_window_inference_slab(vol_slab: torch.Tensor, global_size: Sequence[int], slab: dict,
+                                  roi_size: Sequence[int], sw_batch_size: int, predictor: UNetB200,
+                                  overlap: float = 0.25, mode: str = "constant", sigma_scale: float = 0.125,
+                                  *, return_logits: bool = False):
+    """Multi-GPU form: this rank holds only planes ``[slab.vol_x0, slab.vol_x1)`` of axis 0 of a
+    ``[Cin, *global_size]`` volume (``vol_slab``: ``[Cin, vol_nx, Y, Z]``) and computes the label map
+    (and optionally the logits) of its output planes ``[slab.x0, slab.x1)``; the volume must already be
+    at least ROI-sized along every axis.  Results equal the single-GPU run bit for bit."""
+    net = predictor
+    size3 = tuple(int(s) for s in global_size)
+    sched = make_schedule(size3, net.roi3(roi_size), overlap, mode, sigma_scale)
+    if sched.padded_size != size3:
+        raise ValueError("slab execution needs a volume at least as large as the roi along every axis")
+    vol_nx = int(slab["vol_x1"]) - int(slab["vol_x0"])
+    if tuple(vol_slab.shape) != (net.in_channels, vol_nx, size3[1], size3[2]):
+        raise ValueError(f"vol_slab must be {(net.in_channels, vol_nx, size3[1], size3[2])}, got {tuple(vol_slab.shape)}")
+    nx = int(slab["x1"]) - int(slab["x0"])
+    logits, labels, _ = _sw_run(net, vol_slab.contiguous(), sched, sw_batch_size,
+                                (int(slab["a0_begin"]), int(slab["a0_end"])), (int(slab["vol_x0"]), vol_nx),
+                                (int(slab["x0"]), nx), return_logits, True, False)
+    out = {"labels": labels}
+    if logits is not None:
+        out["logits"] = logits
+    return out
 
 
 def debug_conv(net: UNetB200, conv_index: int, in0: torch.Tensor, in1: Optional[torch.Tensor] = None,

@@ -1,0 +1,276 @@
+"""``segmantic.seg.monai_unet`` prediction API on the B200-native engine.
+
+Mirrors the prediction half of ``/root/reference/src/segmantic/seg/monai_unet.py``:
+
+* ``Net`` (``:99-149``): same constructor arguments / ``hparams`` names (``num_classes``,
+  ``num_channels``, ``spatial_dims``, ``spatial_size``, ``channels``, ``strides``, ``dropout``,
+  ``act``), ``num_classes`` / ``spatial_dims`` properties, ``spatial_size`` default ``[96]*3``,
+  ``load_from_checkpoint(file, **overrides)`` accepting a Lightning ``.ckpt`` (keys ``_model.model.*``
+  + ``hyper_parameters``) or a plain MONAI ``.pth`` (``scripts/extract_unet.py:17-18``);
+  keyword overrides win over saved hyper-parameters as in the reference (``:571-573``).
+* ``predict`` (``:551-725``): same signature; new keyword-only options default to the reference's
+  behaviour (``overlap=0.25``, ``mode="constant"``, ``sw_batch_size=4``, ``precision="fp32"``,
+  ``invert="logits"``).
+* ``predict_volume``: the array-level core of ``predict`` (pre-transforms -> sliding window -> inverse
+  -> argmax) for callers that already hold the voxels (and what ``bench.py`` times end to end).
+
+Training, cross-validation and ensembles are out of scope.  There is no CPU
+fallback: ``gpu_ids=[-1]`` raises.
+"""
+from __future__ import annotations
+
+import json
+import os
+from pathlib import Path
+from types import SimpleNamespace
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import transforms as T
+from .engine import UNetB200, sliding_window_inference
+from .utils import make_device
+
+
+class Net:
+    """Inference-only stand-in for the reference's LightningModule ``Net``."""
+
+    def __init__(self, num_classes: int, num_channels: int = 1, spatial_dims: int = 3,
+                 spatial_size: Sequence[int] = None, channels: tuple = (16, 32, 64, 128, 256),
+                 strides: tuple = (2, 2, 2, 2), dropout: float = 0.0, act: str = "PRELU"):
+        if str(act).upper() != "PRELU":
+            raise ValueError("only act='PRELU' (the reference default) is supported")
+        self.hparams = SimpleNamespace(num_classes=num_classes, num_channels=num_channels,
+                                       spatial_dims=spatial_dims, spatial_size=spatial_size,
+                                       channels=tuple(channels), strides=tuple(strides), dropout=dropout, act=act)
+        self.spatial_size = list(spatial_size) if spatial_size else [96] * 3
+        self._state_dict: Optional[Dict[str, torch.Tensor]] = None
+        self._engines: Dict[tuple, UNetB200] = {}
+        self.device = torch.device("cpu")
+
+    # -- reference properties (monai_unet.py:143-149)
+    @property
+    def num_classes(self) -> int:
+        return int(self.hparams.num_classes)
+
+    @property
+    def spatial_dims(self) -> int:
+        return int(self.hparams.spatial_dims)
+
+    # -- checkpoint handling
+    def load_state_dict(self, state_dict: Dict[str, torch.Tensor]) -> None:
+        self._state_dict = {k: v.detach().cpu() for k, v in state_dict.items() if isinstance(v, torch.Tensor)}
+        self._engines.clear()
+
+    @classmethod
+    def load_from_checkpoint(cls, checkpoint_path, map_location=None, **kwargs) -> "Net":
+        """Lightning ``.ckpt`` or plain ``.pth``; ``kwargs`` override saved hyper-parameters."""
+        try:
+            ckpt = torch.load(str(checkpoint_path), map_location="cpu", weights_only=True)
+        except Exception:
+            ckpt = torch.load(str(checkpoint_path), map_location="cpu", weights_only=False)
+        if isinstance(ckpt, dict) and "state_dict" in ckpt:
+            hp = dict(ckpt.get("hyper_parameters", {}) or {})
+            sd = ckpt["state_dict"]
+        else:
+            hp, sd = {}, ckpt
+        hp.update(kwargs)
+        if "num_classes" not in hp or "num_channels" not in hp:
+            hp.update(_infer_io_channels(sd, hp))
+        allowed = ("num_classes", "num_channels", "spatial_dims", "spatial_size", "channels", "strides",
+                   "dropout", "act")
+        net = cls(**{k: v for k, v in hp.items() if k in allowed})
+        net.load_state_dict(sd)
+        return net
+
+    def freeze(self) -> None:  # the engine is always frozen / eval
+        return None
+
+    def eval(self) -> "Net":
+        return self
+
+    def to(self, device) -> "Net":
+        self.device = torch.device(device)
+        return self
+
+    def engine(self, precision: str = "fp32") -> UNetB200:
+        if self._state_dict is None:
+            raise RuntimeError("Net has no weights: use Net.load_from_checkpoint or load_state_dict")
+        key = (str(self.device), precision)
+        if key not in self._engines:
+            self._engines[key] = UNetB200(self._state_dict, spatial_dims=self.spatial_dims,
+                                          in_channels=int(self.hparams.num_channels),
+                                          out_channels=self.num_classes, channels=self.hparams.channels,
+                                          strides=self.hparams.strides, device=self.device, precision=precision)
+        return self._engines[key]
+
+    def forward(self, x: torch.Tensor, precision: str = "fp32") -> torch.Tensor:
+        return self.engine(precision)(x)
+
+    __call__ = forward
+
+
+def _infer_io_channels(sd, hp) -> dict:
+    """num_channels / num_classes / spatial_dims from the first and last conv of a MONAI UNet state_dict."""
+    keys = {k[len("_model."):] if k.startswith("_model.") else k: v for k, v in sd.items()}
+    first = keys["model.0.conv.unit0.conv.weight"]
+    last = keys["model.2.1.conv.unit0.conv.weight"]
+    out = {"num_channels": int(first.shape[1]), "num_classes": int(last.shape[0])}
+    if "spatial_dims" not in hp:
+        out["spatial_dims"] = first.dim() - 2
+    return out
+
+
+def predict_volume(net: Net, image: torch.Tensor, affine: Optional[np.ndarray] = None,
+                   spacing: Sequence[float] = (), *, overlap: float = 0.25, mode: str = "constant",
+                   sw_batch_size: int = 4, precision: str = "fp32", invert: str = "logits",
+                   normalize: bool = True, crop_foreground: bool = True, return_device: bool = False):
+    """The array-level core of ``predict()`` (``monai_unet.py:589-670``) for ONE image.
+
+    ``image``: ``[C, X, Y, Z]`` (``[C, X, Y]`` for 2-D networks) in ITK index order, any device (host
+    tensors are uploaded).  ``affine``: 4x4 RAS affine of that array (identity direction / unit spacing
+    if omitted).  Applies Orientation(RAS) -> NormalizeIntensity -> CropForeground(image > 0) ->
+    [Spacing(spacing)] -> sliding-window UNet -> inverse -> argmax, and returns the label map as uint8
+    ``[X, Y, Z]`` on the original grid.
+
+    ``invert="logits"`` reproduces the reference (``Invertd`` resamples the C-channel logits
+    trilinearly, then argmax); ``invert="labels"`` is the north-star variant (argmax on the network
+    grid, then nearest-neighbour resampling of the label map).  Without ``spacing`` both are identical.
+    """
+    eng = net.engine(precision)
+    dev = eng.device
+    nd = net.spatial_dims
+    if image.dim() != nd + 1:
+        raise ValueError(f"image must be [C, *spatial({nd})], got {tuple(image.shape)}")
+    img = image.to(dev, dtype=torch.float32, non_blocking=True)
+    if nd == 2:
+        img = img.unsqueeze(1)  # [C, 1, X, Y]: the flat axis leads
+    if affine is None:
+        affine = np.eye(4)
+        if nd == 3:
+            affine[0, 0] = affine[1, 1] = -1.0  # identity-direction ITK image seen in RAS
+    full_shape_itk = tuple(img.shape[1:])
+    if nd == 3:
+        img, aff, orient = T.orientation_ras(img, affine)
+    else:
+        aff, orient = np.asarray(affine, dtype=np.float64), None
+    if normalize:
+        img = T.normalize_intensity(img)
+    oriented_shape = tuple(img.shape[1:])
+    lo, hi = [0, 0, 0], list(oriented_shape)
+    if crop_foreground:
+        lo, hi = T.foreground_bbox(img)
+        if all(h > l for l, h in zip(lo, hi)):
+            img = img[:, lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]].contiguous()
+            shift = np.eye(4)
+            shift[:3, 3] = lo
+            aff = aff @ shift
+        else:
+            lo, hi = [0, 0, 0], list(oriented_shape)
+    record = None
+    if len(spacing) and nd == 3:
+        img, aff, record = T.spacing_forward(img, aff, spacing)
+    net_in = img if nd == 3 else img[:, 0]
+    want_labels = record is None or invert == "labels"
+    res = sliding_window_inference(net_in.unsqueeze(0), net.spatial_size, sw_batch_size, eng, overlap=overlap,
+                                   mode=mode, return_labels=want_labels, return_logits=not want_labels)
+    cropped_shape = tuple(hi[a] - lo[a] for a in range(3))
+    if want_labels:
+        lab = res["labels"][0, 0]
+        if nd == 2:
+            lab = lab.unsqueeze(0)
+        if record is not None:  # nearest-neighbour back-resample of the label map (north-star stage 4)
+            lab = _nearest_back(lab, record)
+    else:
+        lab = T.resample_index_affine_argmax(res["logits"][0], T.spacing_inverse_xform(record), record["src_shape"])
+    if tuple(lab.shape) != oriented_shape:  # inverse CropForeground: zero padding -> label 0
+        full = torch.zeros(oriented_shape, dtype=torch.uint8, device=dev)
+        full[lo[0]:lo[0] + cropped_shape[0], lo[1]:lo[1] + cropped_shape[1], lo[2]:lo[2] + cropped_shape[2]] = lab
+        lab = full
+    if orient is not None:
+        lab = T.orientation_inverse(lab, orient, lead=0)
+    assert tuple(lab.shape) == full_shape_itk
+    if nd == 2:
+        lab = lab[0]
+    eng.check()
+    return lab if return_device else lab.cpu()
+
+
+def _nearest_back(lab: torch.Tensor, record) -> torch.Tensor:
+    """Nearest-neighbour resample of a label map from the network grid back onto the pre-Spacing grid
+    (ITK semantics, ``image/processing.resample_to_ref``)."""
+    from ..image import processing as P
+
+    sp_d, org_d, dir_d = T.ras_affine_to_itk_geometry(record["dst_affine"])
+    sp_s, org_s, dir_s = T.ras_affine_to_itk_geometry(record["src_affine"])
+    moving = P.Image(lab, sp_d, org_d, dir_d)
+    fixed = P.Image(torch.empty(record["src_shape"], dtype=torch.uint8, device="meta"), sp_s, org_s, dir_s)
+    return P.resample_to_ref(moving, fixed, nearest=True).array
+
+
+def predict(model_file: Path, test_images: List[Path], test_labels: Optional[List[Path]] = None,
+            output_dir: Path = None, tissue_dict: Dict[str, int] = None,
+            channels: tuple = (16, 32, 64, 128, 256), strides: tuple = (2, 2, 2, 2), dropout: float = 0.0,
+            spacing: Sequence[float] = [], gpu_ids: List[int] = [], *, overlap: float = 0.25,
+            mode: str = "constant", sw_batch_size: int = 4, precision: str = "fp32",
+            invert: str = "logits") -> None:
+    """Same signature and side effects as ``segmantic.seg.monai_unet.predict`` (``:551-562``):
+    writes ``<output_dir>/<image basename>.nii.gz`` label maps (float32, as ``SaveImaged`` does)."""
+    from ..image import nifti
+
+    model_file = Path(model_file)
+    model_settings_json = model_file.with_suffix(".json")
+    if model_settings_json.exists():
+        print(f"WARNING: Loading legacy model settings from {model_settings_json}")
+        with model_settings_json.open() as json_file:
+            settings = json.load(json_file)
+        net = Net.load_from_checkpoint(f"{model_file}", **settings)
+    else:
+        net = Net.load_from_checkpoint(f"{model_file}", channels=channels, strides=strides, dropout=dropout)
+    num_classes = net.num_classes
+    net.freeze()
+    net.eval()
+    device = make_device(gpu_ids)
+    if device.type != "cuda":
+        raise RuntimeError("segmantic_b200 has no CPU path: pass gpu_ids=[] or a non-negative GPU id")
+    net.to(device)
+
+    tissue_names = [f"{id}" for id in range(num_classes)]
+    if tissue_dict:
+        for name in tissue_dict.keys():
+            idx = tissue_dict[name]
+            if 0 <= idx < num_classes:
+                tissue_names[idx] = name
+    if output_dir:
+        os.makedirs(output_dir, exist_ok=True)
+    have_labels = test_labels is not None and len(test_labels) == len(test_images) and len(test_labels) > 0
+    all_mean_dice = []
+    for i, img_path in enumerate(test_images):
+        img_path = Path(img_path)
+        image, affine, header = nifti.read(img_path)  # [C, X, Y, Z] float32, RAS affine
+        lab = predict_volume(net, torch.from_numpy(image), affine, spacing, overlap=overlap, mode=mode,
+                             sw_batch_size=sw_batch_size, precision=precision, invert=invert)
+        if output_dir:
+            name = img_path.name
+            for ext in (".nii.gz", ".nii", ".nrrd", ".mha", ".mhd"):
+                if name.endswith(ext):
+                    name = name[: -len(ext)]
+                    break
+            nifti.write(Path(output_dir) / f"{name}.nii.gz", lab.numpy().astype(np.float32), affine)
+        if have_labels:
+            ref_lab, _, _ = nifti.read(Path(test_labels[i]))
+            ref_lab = torch.from_numpy(ref_lab[0]).long()
+            dice = []
+            for c in range(1, num_classes):  # include_background=False
+                a, b = (lab.long() == c), (ref_lab == c)
+                den = int(a.sum()) + int(b.sum())
+                dice.append(float("nan") if den == 0 else 2.0 * int((a & b).sum()) / den)
+            print(img_path.name)
+            print("\t" + "\t".join(tissue_names[1:]).expandtabs(30))
+            print("\t" + "\t".join(f"{x}" for x in dice).expandtabs(30))
+            all_mean_dice.append(float(np.nanmean(dice)) if dice else float("nan"))
+    if have_labels and output_dir:
+        out = Path(output_dir) / f"mean_dice_{model_file.stem}_generalized_score.txt"
+        with out.open("w") as f:
+            print(f"Mean dice: {np.nanmean(all_mean_dice)}", file=f)

@@ -18,7 +18,9 @@ def cg8(n, cg, dims, seed, dev, scale=1.0):
 
 def run_case(net, name, idx, in0, in1=None, res=None, fused=False, cg_out2=0):
     try:
+        print(f"START {name}", flush=True)
         ref = engine.debug_conv(net, idx, in0, in1, res, use_tc=False)
+        print("  ref done", flush=True)
         if fused:
             ref2 = engine.debug_conv(net, idx + 2, in0, None, None, use_tc=False)
             out, out2 = engine.debug_conv(net, idx, in0, in1, res, use_tc=True, fused=True, cg_out2=cg_out2)
@@ -52,6 +54,10 @@ def main():
     sd = synthetic_state_dict(3, 1, 10, seed=0)
     net = engine.UNetB200(sd, spatial_dims=3, in_channels=1, out_channels=10, device=dev, precision="bf16")
     results = []
+    if which in ("k1",):
+        results.append(run_case(net, "k1 128->256 bottom.residual 6^3", 14, cg8(1, 16, (6, 6, 6), 9, dev)))
+    if which in ("head",):
+        results.append(run_case(net, "s1 10->10 head conv 32^3", 22, cg8(1, 2, (32, 32, 32), 10, dev)))
     if which in ("all", "s1"):
         # stride-1 3x3x3 convs (indices: d0.unit1=1, d1.unit1=4, d2.unit1=7, d3.unit1=10, bottom 12/13, bottom k1 res=14,
         # up ru: 16, 18, 20, head 22)
