@@ -297,7 +297,10 @@ def run_b200(args):
         pnet.load_state_dict(sd)
         pnet.to(dev)
         host = raw.clone().pin_memory()
-        kw = dict(overlap=OVERLAP, mode=MODE, sw_batch_size=args.sw_batch, precision=args.precision)
+        # crop_foreground=False: CropForegroundd would shrink this synthetic volume to its body ellipsoid
+        # (data dependent); it is disabled so that e2e runs the same 125 windows as `value`.
+        kw = dict(overlap=OVERLAP, mode=MODE, sw_batch_size=args.sw_batch, precision=args.precision,
+                  crop_foreground=False)
         for _ in range(2):
             predict_volume(pnet, host, None, (), **kw)
         barrier()

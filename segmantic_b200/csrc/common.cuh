@@ -75,6 +75,9 @@ enum { OUT_CG8 = 0, OUT_BLEND = 1, OUT_PLANAR = 2 };
 int fp32_conv_cout_tile(bool transposed);
 int launch_conv_fp32(const ConvArgs& a, bool bf16_storage, bool in_planar, int out_kind, cudaStream_t st);
 int launch_convT_fp32(const ConvArgs& a, bool bf16_storage, cudaStream_t st);
+// fused stem (first down block's unit0 + residual-branch conv, planar fp32 input)
+int stem_cout_tile();
+int launch_stem(const ConvArgs& a, int cgA, int cgB, void* outA, void* outB, bool bf16_storage, cudaStream_t st);
 
 // ---- bf16 tcgen05 family (conv_tc.cu)
 struct TcConvPlan;

@@ -48,7 +48,7 @@ struct KArgs {
   int P, nslab;
   int row_first, ntiles, tpc, nchunks, nbuf, ncls, cols_per_buf, tmem_cols;
   int N, nblk, G, ngroups, nstages, resident;
-  const uint32_t* blkdesc;
+  int blk_off;        // offset of this conv's K-block descriptors in c_blk
   const __nv_bfloat16* w;
   const float* bias;
   __nv_bfloat16* outA;
@@ -169,6 +169,33 @@ __device__ __forceinline__ uint4 pack8(const float v[8]) {
 }
 
 // ------------------------------------------------------------------------------------------ kernel
+// K-block descriptors of every distinct (mode, kernel, channel-pair count) live in constant memory so
+// the MMA warp reads them through the uniform datapath (no per-lane waterfall around tcgen05.mma).
+constexpr int kBlkConst = 12288;
+__constant__ uint32_t c_blk[kBlkConst];
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// Bounded wait for the uniform (all-lanes) roles: a timeout aborts the kernel instead of hanging.
+__device__ __forceinline__ void mbar_wait_or_trap(uint32_t bar, uint32_t parity, int* err, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > kWaitCycles) {
+      atomicExch(err, code);
+      __trap();
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const KArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -183,8 +210,7 @@ __global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const KArgs a) {
   uint8_t* a_smem = smem;
   const int a_bytes = a.a_units * 16;
   uint8_t* w_smem = smem + a_bytes;
-  int2* table = reinterpret_cast<int2*>(w_smem + a.nstages * a.w_stage_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(table) + ((a.nblk * 8 + 15) & ~15));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_smem + a.nstages * a.w_stage_bytes);
   // bars: [0,nstages) wfull, [nstages,2nstages) wempty, then tfull[2], tempty[2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * a.nstages + 4);
   const uint32_t bar0 = smem_u32(bars);
@@ -211,49 +237,41 @@ __global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const KArgs a) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
 
-  // ---- K-block table: A start (16-byte units from the brick base) + class/first flags
-  const int H12 = a.H[1] * a.H[2];
-  for (int b = tid; b < a.nblk; b += kThreads) {
-    const uint32_t d = __ldg(a.blkdesc + b);
-    const int s0 = (int)(d & 3u) - 1, s1 = (int)((d >> 2) & 3u) - 1, s2 = (int)((d >> 4) & 3u) - 1;
-    const int slab = (d >> 6) & 7u, cls = (d >> 9) & 7u, first = (d >> 12) & 1u, cgpair = (d >> 16) & 0xffu;
-    const int a16 = (slab * a.cgin + cgpair * 2) * a.P + a.row_first + s0 * H12 + s1 * a.H[2] + s2;
-    table[b] = make_int2(a16, cls | (first << 8));
-  }
-
-  // ---- gather the halo brick: [slab][cg][P] x 16 B, zero fill outside the window
+  // ---- gather the halo brick: [slab][cg][h0][h1][h2] x 16 B, zero fill outside the window.
+  // One warp per brick row (fixed slab, cg, h0, h1), lanes along h2 -> no per-element div/mod and
+  // 16-byte requests that are contiguous in global memory for stride-1 bricks.
   {
     const long long ivox = (long long)a.id[0] * a.id[1] * a.id[2];
-    const int items = a.nslab * a.cgin * a.P;
     const uint32_t a_base = smem_u32(a_smem);
     const int ib0 = org[0] * a.ibase_mul[0] + a.ioff[0], ib1 = org[1] * a.ibase_mul[1] + a.ioff[1],
               ib2 = org[2] * a.ibase_mul[2] + a.ioff[2];
-    for (int it = tid; it < items; it += kThreads) {
-      const int pos = it % a.P;
-      const int sc = it / a.P;
-      const int cg = sc % a.cgin, slab = sc / a.cgin;
-      const int h2 = pos % a.H[2];
-      const int h01 = pos / a.H[2];
-      const int h1 = h01 % a.H[1], h0 = h01 / a.H[1];
-      // parity bits of the slab, most significant = axis 0 (only axes with par==2 consume a bit)
-      int bits = slab;
+    const int rows_per_sc = a.H[0] * a.H[1];
+    const int nrows = a.nslab * a.cgin * rows_per_sc;
+    for (int row = warp; row < nrows; row += kThreads / 32) {
+      const int sc = row / rows_per_sc, h01 = row - sc * rows_per_sc;
+      const int slab = sc / a.cgin, cg = sc - slab * a.cgin;
+      const int h0 = h01 / a.H[1], h1 = h01 - h0 * a.H[1];
+      int bits = slab;  // parity bits, least significant = axis 2 (only axes with par==2 consume a bit)
       const int r2 = a.par[2] == 2 ? (bits & 1) : 0;
       bits >>= (a.par[2] == 2);
       const int r1 = a.par[1] == 2 ? (bits & 1) : 0;
       bits >>= (a.par[1] == 2);
       const int r0 = a.par[0] == 2 ? (bits & 1) : 0;
-      const int i0 = ib0 + a.imul[0] * h0 + r0, i1 = ib1 + a.imul[1] * h1 + r1, i2 = ib2 + a.imul[2] * h2 + r2;
-      const bool ok = i0 >= 0 && i0 < a.id[0] && i1 >= 0 && i1 < a.id[1] && i2 >= 0 && i2 < a.id[2];
-      const __nv_bfloat16* src = a.in0;
-      if (ok) {
-        const long long ipos = ((long long)i0 * a.id[1] + i1) * a.id[2] + i2;
-        src = (cg < a.cg0) ? a.in0 + (((long long)n * a.cg0 + cg) * ivox + ipos) * 8
-                           : a.in1 + (((long long)n * a.cg1 + (cg - a.cg0)) * ivox + ipos) * 8;
+      const int i0 = ib0 + a.imul[0] * h0 + r0, i1 = ib1 + a.imul[1] * h1 + r1;
+      const bool ok01 = i0 >= 0 && i0 < a.id[0] && i1 >= 0 && i1 < a.id[1];
+      const __nv_bfloat16* base = (cg < a.cg0) ? a.in0 + ((long long)n * a.cg0 + cg) * ivox * 8
+                                               : a.in1 + ((long long)n * a.cg1 + (cg - a.cg0)) * ivox * 8;
+      const long long rowoff = ((long long)i0 * a.id[1] + i1) * a.id[2];
+      const uint32_t dst_row = a_base + (uint32_t)(sc * a.P + h01 * a.H[2]) * 16u;
+      for (int h2 = lane; h2 < a.H[2]; h2 += 32) {
+        const int i2 = ib2 + a.imul[2] * h2 + r2;
+        const bool ok = ok01 && i2 >= 0 && i2 < a.id[2];
+        const __nv_bfloat16* src = ok ? base + (rowoff + i2) * 8 : a.in0;
+        cp_async16(dst_row + (uint32_t)h2 * 16u, src, ok ? 16u : 0u);
       }
-      cp_async16(a_base + (uint32_t)it * 16u, src, ok ? 16u : 0u);
     }
     // zero the tail the last M tile may read (keeps garbage rows finite; they are discarded anyway)
-    for (int it = items + tid; it < a.a_units; it += kThreads)
+    for (int it = a.nslab * a.cgin * a.P + tid; it < a.a_units; it += kThreads)
       *reinterpret_cast<uint4*>(a_smem + (size_t)it * 16) = make_uint4(0, 0, 0, 0);
     asm volatile("cp.async.wait_all;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core reads
@@ -283,48 +301,45 @@ __global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const KArgs a) {
       }
     }
   } else if (warp == 4) {
-    // ================= MMA issuer (single thread) =================
-    if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=bf16, K-major both, N>>3 at [17,23), M>>4 at [24,29)
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t a_base16 = smem_u32(a_smem) >> 4;
-      const uint32_t w_base16 = smem_u32(w_smem) >> 4;
-      bool ok = true;
-      for (int chunk = 0; chunk < a.nchunks && ok; ++chunk) {
-        const int buf = a.nbuf == 2 ? (chunk & 1) : 0;
-        const int use = a.nbuf == 2 ? (chunk >> 1) : chunk;
-        if (use > 0) ok = mbar_wait(TEMPTY(buf), (uint32_t)(use - 1) & 1u, a.error_flag, 2);
-        if (!ok) break;
-        tc_fence_after();
-        const int tiles_here = min(a.tpc, a.ntiles - chunk * a.tpc);
-        for (int g = 0; g < a.ngroups && ok; ++g) {
-          int stage;
-          if (!a.resident || chunk == 0) {
-            const int it = a.resident ? g : chunk * a.ngroups + g;
-            stage = it % a.nstages;
-            ok = mbar_wait(WFULL(stage), (uint32_t)(it / a.nstages) & 1u, a.error_flag, 3);
-            if (!ok) break;
-            tc_fence_after();
-          } else {
-            stage = g;
-          }
-          const int bend = min(a.nblk, (g + 1) * a.G);
-          for (int b = g * a.G; b < bend; ++b) {
-            const int2 e = table[b];
-            const uint64_t bdesc =
-                make_desc(w_base16 + (uint32_t)(stage * a.w_stage_bytes + (b - g * a.G) * N * 32) / 16u, (uint32_t)N, 8u);
-            const uint32_t acc = (e.y >> 8) ? 0u : 1u;
-            const uint32_t col = (uint32_t)(buf * a.cols_per_buf + (e.y & 0xff) * N);
-            for (int t = 0; t < tiles_here; ++t) {
-              const uint64_t adesc =
-                  make_desc(a_base16 + (uint32_t)(e.x + (chunk * a.tpc + t) * 128), (uint32_t)a.P, 8u);
-              tc_mma(tmem_base + col + (uint32_t)(t * a.ncls * N), adesc, bdesc, idesc, acc);
-            }
-          }
-          if (!a.resident) tc_commit(WEMPTY(stage));
+    // ================= MMA issuer: the whole warp runs the (uniform) loop, one elected lane issues ======
+    // instruction descriptor: D=f32, A=B=bf16, K-major both, N>>3 at [17,23), M>>4 at [24,29)
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t a_base16 = smem_u32(a_smem) >> 4;
+    const uint32_t w_base16 = smem_u32(w_smem) >> 4;
+    const int H12 = a.H[1] * a.H[2];
+    for (int chunk = 0; chunk < a.nchunks; ++chunk) {
+      const int buf = a.nbuf == 2 ? (chunk & 1) : 0;
+      const int use = a.nbuf == 2 ? (chunk >> 1) : chunk;
+      if (use > 0) mbar_wait_or_trap(TEMPTY(buf), (uint32_t)(use - 1) & 1u, a.error_flag, 2);
+      tc_fence_after();
+      const int tiles_here = min(a.tpc, a.ntiles - chunk * a.tpc);
+      for (int g = 0; g < a.ngroups; ++g) {
+        int stage = g;
+        if (!a.resident || chunk == 0) {
+          const int it = a.resident ? g : chunk * a.ngroups + g;
+          stage = it % a.nstages;
+          mbar_wait_or_trap(WFULL(stage), (uint32_t)(it / a.nstages) & 1u, a.error_flag, 3);
+          tc_fence_after();
         }
-        if (ok) tc_commit(TFULL(buf));
+        const int bend = min(a.nblk, (g + 1) * a.G);
+        for (int b = g * a.G; b < bend; ++b) {
+          const uint32_t d = c_blk[a.blk_off + b];
+          const int s0 = (int)(d & 3u) - 1, s1 = (int)((d >> 2) & 3u) - 1, s2 = (int)((d >> 4) & 3u) - 1;
+          const int slab = (d >> 6) & 7u, cls = (d >> 9) & 7u, cgpair = (d >> 16) & 0xffu;
+          const uint32_t acc = ((d >> 12) & 1u) ? 0u : 1u;
+          const int a16 = (slab * a.cgin + cgpair * 2) * a.P + a.row_first + s0 * H12 + s1 * a.H[2] + s2;
+          const uint64_t bdesc =
+              make_desc(w_base16 + (uint32_t)(stage * a.w_stage_bytes + (b - g * a.G) * N * 32) / 16u, (uint32_t)N, 8u);
+          const uint32_t col = tmem_base + (uint32_t)(buf * a.cols_per_buf + cls * N);
+          for (int t = 0; t < tiles_here; ++t) {
+            const uint64_t adesc = make_desc(a_base16 + (uint32_t)(a16 + (chunk * a.tpc + t) * 128), (uint32_t)a.P, 8u);
+            if (elect_one()) tc_mma(col + (uint32_t)(t * a.ncls * N), adesc, bdesc, idesc, acc);
+          }
+        }
+        if (!a.resident && elect_one()) tc_commit(WEMPTY(stage));
       }
+      if (elect_one()) tc_commit(TFULL(buf));
+      __syncwarp();
     }
   } else {
     // ================= epilogue warps 0..3: TMEM lanes 32*warp .. 32*warp+31 =================
@@ -333,18 +348,38 @@ __global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const KArgs a) {
     for (int chunk = 0; chunk < a.nchunks && ok; ++chunk) {
       const int buf = a.nbuf == 2 ? (chunk & 1) : 0;
       const int use = a.nbuf == 2 ? (chunk >> 1) : chunk;
-      ok = mbar_wait(TFULL(buf), (uint32_t)use & 1u, a.error_flag, 4);
-      if (!ok) break;
-      tc_fence_after();
       const int tiles_here = min(a.tpc, a.ntiles - chunk * a.tpc);
-      for (int t = 0; t < tiles_here; ++t) {
+      // head (blend) path: the accumulator read-modify-write does not depend on the MMA results, so the
+      // old values of the first tile are fetched BEFORE waiting for the tensor core.
+      float oldv[16];
+      auto row_geom = [&](int t, int& o0, int& o1, int& o2) -> bool {
         const int p = a.row_first + (chunk * a.tpc + t) * 128 + warp * 32 + lane;
         const int h2 = p % a.H[2];
         const int h01 = p / a.H[2];
         const int h1 = h01 % a.H[1], h0 = h01 / a.H[1];
-        const int r0 = org[0] + h0 - a.lo[0], r1 = org[1] + h1 - a.lo[1], r2 = org[2] + h2 - a.lo[2];
-        const bool valid = h0 >= a.lo[0] && h0 < a.lo[0] + a.t[0] && h1 >= a.lo[1] && h1 < a.lo[1] + a.t[1] &&
-                           h2 >= a.lo[2] && h2 < a.lo[2] + a.t[2] && r0 < a.rd[0] && r1 < a.rd[1] && r2 < a.rd[2];
+        o0 = org[0] + h0 - a.lo[0], o1 = org[1] + h1 - a.lo[1], o2 = org[2] + h2 - a.lo[2];
+        return h0 >= a.lo[0] && h0 < a.lo[0] + a.t[0] && h1 >= a.lo[1] && h1 < a.lo[1] + a.t[1] &&
+               h2 >= a.lo[2] && h2 < a.lo[2] + a.t[2] && o0 < a.rd[0] && o1 < a.rd[1] && o2 < a.rd[2];
+      };
+      auto blend_prefetch = [&](int t) {
+        int o0, o1, o2;
+        const bool v = row_geom(t, o0, o1, o2);
+        const int g0 = a.wo[0] + o0;
+        if (v && g0 >= 0 && g0 < a.ad0) {
+          const long long off = ((long long)g0 * a.ad1 + (a.wo[1] + o1)) * a.ad2 + (a.wo[2] + o2);
+#pragma unroll
+          for (int c = 0; c < 16; ++c)
+            if (c < a.c_real) oldv[c] = __ldcg(a.pl_out + c * a.pl_cstride + off);
+        }
+      };
+      const bool blend = a.out_kind == OUT_BLEND && N == 16;
+      if (blend) blend_prefetch(0);
+      ok = mbar_wait(TFULL(buf), (uint32_t)use & 1u, a.error_flag, 4);
+      if (!ok) break;
+      tc_fence_after();
+      for (int t = 0; t < tiles_here; ++t) {
+        int r0, r1, r2;
+        const bool valid = row_geom(t, r0, r1, r2);
         for (int cls = 0; cls < a.ncls; ++cls) {
           int o0 = r0, o1 = r1, o2 = r2;
           if (a.mode == MODE_T2) {
@@ -361,7 +396,6 @@ __global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const KArgs a) {
           for (int piece = 0; piece < N / 16; ++piece) {
             uint32_t raw[16];
             tc_ld16(tcol + piece * 16, raw);  // warp-collective: every lane executes it
-            if (!valid) continue;
             const int cbase = coblk * N + piece * 16;  // fused output channel of raw[0]
             const int gcg = cbase >> 3;
             const bool segA = gcg < a.segA_cg;
@@ -373,7 +407,7 @@ __global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const KArgs a) {
               v[c] = x;
             }
             if (segA) {
-              if (a.res) {
+              if (a.res && valid) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                   float r[8];
@@ -385,38 +419,44 @@ __global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const KArgs a) {
                 }
               }
               if (a.out_kind == OUT_CG8) {
+                if (valid) {
 #pragma unroll
-                for (int h = 0; h < 2; ++h)
-                  if (gcg + h < a.cgA)
-                    *reinterpret_cast<uint4*>(a.outA + (((long long)n * a.cgA + gcg + h) * ovox + opos) * 8) =
-                        pack8(v + h * 8);
-              } else {
-                long long off;
-                float imw = 1.f;
-                bool pl_ok = true;
-                if (a.out_kind == OUT_BLEND) {
-                  const int g0 = a.wo[0] + o0;
-                  pl_ok = g0 >= 0 && g0 < a.ad0;
-                  off = ((long long)g0 * a.ad1 + (a.wo[1] + o1)) * a.ad2 + (a.wo[2] + o2);
-                  imw = fmaxf(__fmul_rn(__fmul_rn(a.imap0[o0], a.imap1[o1]), a.imap2[o2]), a.imap_floor);
-                } else {
-                  off = (long long)n * a.pl_nstride + opos;
+                  for (int h = 0; h < 2; ++h)
+                    if (gcg + h < a.cgA)
+                      *reinterpret_cast<uint4*>(a.outA + (((long long)n * a.cgA + gcg + h) * ovox + opos) * 8) =
+                          pack8(v + h * 8);
                 }
+              } else if (a.out_kind == OUT_BLEND) {
+                const int g0 = a.wo[0] + o0;
+                const bool pl_ok = valid && g0 >= 0 && g0 < a.ad0;
+                const long long off = ((long long)g0 * a.ad1 + (a.wo[1] + o1)) * a.ad2 + (a.wo[2] + o2);
+                float res_v[16];
+                if (pl_ok) {
+                  const float imw =
+                      fmaxf(__fmul_rn(__fmul_rn(a.imap0[o0], a.imap1[o1]), a.imap2[o2]), a.imap_floor);
+                  if (!blend) {
+#pragma unroll
+                    for (int c = 0; c < 16; ++c)
+                      if (cbase + c < a.c_real) oldv[c] = __ldcg(a.pl_out + (cbase + c) * a.pl_cstride + off);
+                  }
+#pragma unroll
+                  for (int c = 0; c < 16; ++c)  // seg *= w; out += seg (two roundings, as MONAI)
+                    res_v[c] = __fadd_rn(oldv[c], __fmul_rn(v[c], imw));
+                }
+                // fetch the next tile's accumulator values before storing (keeps ~C loads in flight)
+                if (blend && t + 1 < tiles_here) blend_prefetch(t + 1);
                 if (pl_ok) {
 #pragma unroll
-                  for (int c = 0; c < 16; ++c) {
-                    const int ch = cbase + c;
-                    if (ch < a.c_real) {
-                      float* dst = a.pl_out + ch * a.pl_cstride + off;
-                      if (a.out_kind == OUT_BLEND)
-                        *dst = __fadd_rn(*dst, __fmul_rn(v[c], imw));
-                      else
-                        *dst = v[c];
-                    }
-                  }
+                  for (int c = 0; c < 16; ++c)
+                    if (cbase + c < a.c_real) __stcg(a.pl_out + (cbase + c) * a.pl_cstride + off, res_v[c]);
                 }
+              } else if (valid) {
+                const long long off = (long long)n * a.pl_nstride + opos;
+#pragma unroll
+                for (int c = 0; c < 16; ++c)
+                  if (cbase + c < a.c_real) a.pl_out[(cbase + c) * a.pl_cstride + off] = v[c];
               }
-            } else {
+            } else if (valid) {
               const int bcg = gcg - a.segA_cg;
 #pragma unroll
               for (int h = 0; h < 2; ++h)
@@ -457,23 +497,37 @@ bool tc_supported(const sgm_conv_desc& d) {
   return (d.kernel == 3 || d.kernel == 1) && (d.stride == 1 || d.stride == 2);
 }
 
-struct BlkCache {
-  const TcConv* key;
-  uint32_t* dev;
-};
-static std::vector<BlkCache> g_blk_cache;
-
 void tc_free(TcConv* c) {
   if (!c) return;
-  for (size_t i = 0; i < g_blk_cache.size(); ++i)
-    if (g_blk_cache[i].key == c) {
-      cudaFree(g_blk_cache[i].dev);
-      g_blk_cache.erase(g_blk_cache.begin() + i);
-      break;
-    }
   if (c->w) cudaFree(c->w);
   if (c->bias) cudaFree(c->bias);
   delete c;
+}
+
+// K-block descriptor tables depend only on (mode, kernel extents, channel pairs): identical tables of
+// different convolutions / networks share one slice of the constant bank.
+struct BlkSlice {
+  std::vector<uint32_t> words;
+  int off;
+};
+static std::vector<BlkSlice> g_blk_slices;
+static int g_blk_used = 0;
+
+static int blk_offset(const TcConv& c) {
+  std::vector<uint32_t> d(c.blocks.size());
+  for (size_t i = 0; i < d.size(); ++i) {
+    const KBlock& b = c.blocks[i];
+    d[i] = (uint32_t)(b.shift[0] + 1) | ((uint32_t)(b.shift[1] + 1) << 2) | ((uint32_t)(b.shift[2] + 1) << 4) |
+           ((uint32_t)b.slab << 6) | ((uint32_t)b.cls << 9) | ((uint32_t)b.first << 12) | ((uint32_t)b.cgpair << 16);
+  }
+  for (auto& sl : g_blk_slices)
+    if (sl.words == d) return sl.off;
+  if (g_blk_used + (int)d.size() > kBlkConst) return -1;
+  const int off = g_blk_used;
+  if (cudaMemcpyToSymbol(c_blk, d.data(), d.size() * 4, (size_t)off * 4, cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+  g_blk_used += (int)d.size();
+  g_blk_slices.push_back({d, off});
+  return off;
 }
 
 // Weight element of the (possibly flipped / transposed) conv: W(co, ci, tap)
@@ -617,25 +671,14 @@ int tc_pack(const sgm_conv_desc* m, const sgm_conv_desc* second, int spatial_dim
   }
   cudaMemcpy(c->w, w.data(), w.size() * 2, cudaMemcpyHostToDevice);
   cudaMemcpy(c->bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice);
+  c->blk_off = blk_offset(*c);
+  if (c->blk_off < 0) {
+    set_error("tc_pack: K-block descriptor bank exhausted / upload failed");
+    tc_free(c);
+    return SGM_ERR_CUDA;
+  }
   *out = c;
   return SGM_OK;
-}
-
-// Device copy of the block descriptors: a small side allocation created lazily (one per conv).
-static uint32_t* blkdesc_dev(const TcConv& c) {
-  for (auto& e : g_blk_cache)
-    if (e.key == &c) return e.dev;
-  std::vector<uint32_t> d(c.blocks.size());
-  for (size_t i = 0; i < d.size(); ++i) {
-    const KBlock& b = c.blocks[i];
-    d[i] = (uint32_t)(b.shift[0] + 1) | ((uint32_t)(b.shift[1] + 1) << 2) | ((uint32_t)(b.shift[2] + 1) << 4) |
-           ((uint32_t)b.slab << 6) | ((uint32_t)b.cls << 9) | ((uint32_t)b.first << 12) | ((uint32_t)b.cgpair << 16);
-  }
-  uint32_t* dev = nullptr;
-  if (cudaMalloc(&dev, d.size() * 4) != cudaSuccess) return nullptr;
-  cudaMemcpy(dev, d.data(), d.size() * 4, cudaMemcpyHostToDevice);
-  g_blk_cache.push_back({&c, dev});
-  return dev;
 }
 
 int tc_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t st) {
@@ -695,7 +738,7 @@ int tc_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t
   static const int cand[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64, 96};
   double best = 1e30;
   int bt[3] = {0, 0, 0};
-  const int fixed_bytes = a.nstages * a.w_stage_bytes + round_up(nblk * 8, 16) + (2 * a.nstages + 4) * 8 + 16 + 256;
+  const int fixed_bytes = a.nstages * a.w_stage_bytes + (2 * a.nstages + 4) * 8 + 16 + 256;
   for (int c0 : cand)
     for (int c1 : cand)
       for (int c2 : cand) {
@@ -739,8 +782,7 @@ int tc_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t
   a.a_units = round_up(a.a_units, 8);
   const int smem_bytes = a.a_units * 16 + fixed_bytes;
 
-  a.blkdesc = blkdesc_dev(c);
-  SGM_REQUIRE(a.blkdesc, SGM_ERR_CUDA, "tc_launch: block table upload failed");
+  a.blk_off = c.blk_off;
   a.w = c.w, a.bias = c.bias;
   a.outA = (__nv_bfloat16*)io.outA, a.cgA = io.cgA, a.outB = (__nv_bfloat16*)io.outB, a.cgB = io.cgB;
   a.segA_cg = c.segA_cg, a.actA = c.actA, a.alphaA = c.alphaA;

@@ -37,6 +37,7 @@ struct TcConv {
   int actA = 0;
   float alphaA = 0.f;
   int c_real = 0;             // real (unpadded) channels of segment A
+  int blk_off = -1;           // slice of the constant K-block bank
 };
 
 struct TcIO {

@@ -47,6 +47,8 @@ struct sgm_unet {
   int64_t last_launches = 0;
   // tcgen05 dispatch mask (env SGM_TC, default all): 1 stride-1 convs, 2 strided down convs (fused
   // with the residual branch), 4 transposed convs, 8 head (conv + blend epilogue)
+  float* stem_w = nullptr;     // fused stem: [coblk][tap][ci][STEM_CO] + bias
+  float* stem_bias = nullptr;
   int tc_mask = 15;
   int* err_dev = nullptr;  // device flag raised by a tcgen05 pipeline timeout
   // optional per-convolution CUDA-event timing (sgm_unet_set_profiling)
@@ -113,6 +115,43 @@ int pack_fp32(const sgm_conv_desc& d, PackedConv& pc, bool round_bf16) {
   }
   SGM_CUDA_CHECK(cudaMemcpy(pc.w32, w.data(), nw * sizeof(float), cudaMemcpyHostToDevice));
   SGM_CUDA_CHECK(cudaMemcpy(pc.bias, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return SGM_OK;
+}
+
+// ---- fused stem packing: [coblk][tap][ci][STEM_CO]; fused channel f < cgA*8 is unit0's (padded),
+// the rest the residual-branch conv's.  A k=1 residual conv (stride-1 stem) sits on the centre tap.
+int pack_stem(const sgm_conv_desc& u0, const sgm_conv_desc& rs, const PackedConv& p0, const PackedConv& pr,
+              bool round_bf16, float** w_dev, float** b_dev) {
+  if (rs.kind != SGM_KIND_CONV) return SGM_OK;  // identity residual: no fused stem (rejected at run time)
+  const int co_t = stem_cout_tile();
+  const int ntaps = p0.k[0] * p0.k[1] * p0.k[2];
+  const int nf = (p0.cgout + pr.cgout) * 8;
+  const int ncoblk = ceil_div(nf, co_t);
+  std::vector<float> w((size_t)ncoblk * ntaps * u0.cin * co_t, 0.f), b((size_t)ncoblk * co_t, 0.f);
+  const int rtaps = pr.k[0] * pr.k[1] * pr.k[2];
+  for (int f = 0; f < nf; ++f) {
+    const bool isA = f < p0.cgout * 8;
+    const sgm_conv_desc& src = isA ? u0 : rs;
+    const int co = isA ? f : f - p0.cgout * 8;
+    if (co >= src.cout) continue;
+    b[f] = src.bias[co];
+    for (int ci = 0; ci < u0.cin; ++ci)
+      for (int t = 0; t < ntaps; ++t) {
+        float v;
+        if (isA || rtaps == ntaps) {
+          v = src.weight[((size_t)co * src.cin + ci) * ntaps + t];
+        } else {  // k=1 residual: centre tap only
+          v = (t == ntaps / 2) ? src.weight[(size_t)co * src.cin + ci] : 0.f;
+        }
+        w[(((size_t)(f / co_t) * ntaps + t) * u0.cin + ci) * co_t + f % co_t] = round_bf16 ? bf16_round(v) : v;
+      }
+  }
+  if (cudaMalloc(w_dev, w.size() * 4) != cudaSuccess || cudaMalloc(b_dev, b.size() * 4) != cudaSuccess) {
+    set_error("cudaMalloc of stem weights failed");
+    return SGM_ERR_CUDA;
+  }
+  SGM_CUDA_CHECK(cudaMemcpy(*w_dev, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+  SGM_CUDA_CHECK(cudaMemcpy(*b_dev, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
   return SGM_OK;
 }
 
@@ -273,23 +312,19 @@ int run_network(sgm_unet* net, const float* vol, long long vol_cstride, int vd1,
       t = alloc(u0.cgout, od);
       r = alloc(rs.cgout, od);
       if (!dry) {
-        for (int which = 0; which < 2; ++which) {
-          const PackedConv& pc = which ? rs : u0;
-          ConvArgs a;
-          memset(&a, 0, sizeof(a));
-          a.in0 = vol, a.cg0 = pc.cgin, a.cin_real = pc.cin, a.n = n;
-          for (int q = 0; q < 3; ++q) {
-            a.id[q] = roi[q], a.od[q] = od[q];
-            a.k[q] = pc.k[q], a.s[q] = pc.s[q], a.pad[q] = pc.pad[q];
-          }
-          a.w = pc.w32, a.bias = pc.bias, a.cout_groups = pc.cgout, a.act = pc.act, a.alpha = pc.alpha;
-          a.out = which ? r.p : t.p;
-          a.vol_cstride = vol_cstride, a.vd1 = vd1, a.vd2 = vd2, a.win_origin = win_origin_dev;
-          net->last_launches++;
-          Prof prof(net, st, &pc, dry);
-          int rc = launch_conv_fp32(a, bf16, true, OUT_CG8, st);
-          if (rc) return rc;
+        ConvArgs a;
+        memset(&a, 0, sizeof(a));
+        a.in0 = vol, a.cin_real = u0.cin, a.n = n;
+        for (int q = 0; q < 3; ++q) {
+          a.id[q] = roi[q], a.od[q] = od[q];
+          a.k[q] = u0.k[q], a.s[q] = u0.s[q], a.pad[q] = u0.pad[q];
         }
+        a.w = net->stem_w, a.bias = net->stem_bias, a.act = u0.act, a.alpha = u0.alpha;
+        a.vol_cstride = vol_cstride, a.vd1 = vd1, a.vd2 = vd2, a.win_origin = win_origin_dev;
+        net->last_launches++;
+        Prof prof(net, st, &u0, dry);
+        int rc = launch_stem(a, t.cg, r.cg, t.p, r.p, bf16, st);
+        if (rc) return rc;
       }
     } else {
       int rc = conv_pair(u0, rs, cur, t, r);
@@ -411,6 +446,8 @@ extern "C" void sgm_unet_destroy(sgm_unet* net) {
     tc::tc_free(c.tc_fused);
   }
   if (net->err_dev) cudaFree(net->err_dev);
+  if (net->stem_w) cudaFree(net->stem_w);
+  if (net->stem_bias) cudaFree(net->stem_bias);
   for (auto& e : net->prof_pending) cudaEventDestroy(e.a), cudaEventDestroy(e.b);
   for (auto& e : net->ev_pool) cudaEventDestroy(e);
   delete net;
@@ -490,6 +527,13 @@ extern "C" int32_t sgm_unet_create(const sgm_unet_desc* d, sgm_unet** out) {
     if (!rc && bf16 && i >= 3 && i < 3 * d->n_levels && i % 3 == 0 && c.stride == 2 &&
         d->convs[i + 2].kind == SGM_KIND_CONV && d->convs[i + 2].kernel == c.kernel && tc::tc_supported(c))
       rc = tc::tc_pack(&c, &d->convs[i + 2], d->spatial_dims, &pc.tc_fused);
+    if (rc) {
+      sgm_unet_destroy(net);
+      return rc;
+    }
+  }
+  {
+    int rc = pack_stem(d->convs[0], d->convs[2], net->convs[0], net->convs[2], bf16, &net->stem_w, &net->stem_bias);
     if (rc) {
       sgm_unet_destroy(net);
       return rc;
