@@ -23,6 +23,8 @@
 // two CTAs per SM overlap brick loads with the other CTA's MMAs.
 #include "conv_tc.cuh"
 
+#include <cuda.h>  // CUtensorMap (types only; the encoder is resolved through cudaGetDriverEntryPoint)
+
 #include <algorithm>
 #include <stdlib.h>
 #include <string.h>
@@ -68,6 +70,8 @@ struct KArgs {
   const float* imap2;
   float imap_floor;
   int c_real;
+  int use_tma;        // brick loaded by TMA (cp.async.bulk.tensor) instead of the cp.async gather
+  int box_bytes;      // bytes one TMA box (one channel group of the brick) deposits
   int a_units;        // 16-byte units reserved for the A region
   int w_stage_bytes;
   int* error_flag;
@@ -196,7 +200,16 @@ __device__ __forceinline__ void mbar_wait_or_trap(uint32_t bar, uint32_t parity,
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const KArgs a) {
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+tc_conv_kernel(const KArgs a, const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int coblk = blockIdx.y, n = blockIdx.z;
@@ -212,12 +225,13 @@ __global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const KArgs a) {
   uint8_t* w_smem = smem + a_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(w_smem + a.nstages * a.w_stage_bytes);
   // bars: [0,nstages) wfull, [nstages,2nstages) wempty, then tfull[2], tempty[2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * a.nstages + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * a.nstages + 5);
   const uint32_t bar0 = smem_u32(bars);
   auto WFULL = [&](int s) { return bar0 + 8u * s; };
   auto WEMPTY = [&](int s) { return bar0 + 8u * (a.nstages + s); };
   auto TFULL = [&](int b) { return bar0 + 8u * (2 * a.nstages + b); };
   auto TEMPTY = [&](int b) { return bar0 + 8u * (2 * a.nstages + 2 + b); };
+  const uint32_t ABAR = bar0 + 8u * (2 * a.nstages + 4);  // brick landed (TMA path)
 
   if (warp == 4 && lane == 0) {
     for (int s = 0; s < a.nstages; ++s) {
@@ -228,6 +242,7 @@ __global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const KArgs a) {
       mbar_init(TFULL(b), 1);
       mbar_init(TEMPTY(b), 128);
     }
+    mbar_init(ABAR, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 5) {
@@ -240,17 +255,20 @@ __global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const KArgs a) {
   // ---- gather the halo brick: [slab][cg][h0][h1][h2] x 16 B, zero fill outside the window.
   // One warp per brick row (fixed slab, cg, h0, h1), lanes along h2 -> no per-element div/mod and
   // 16-byte requests that are contiguous in global memory for stride-1 bricks.
-  {
+  if (!a.use_tma) {
     const long long ivox = (long long)a.id[0] * a.id[1] * a.id[2];
     const uint32_t a_base = smem_u32(a_smem);
     const int ib0 = org[0] * a.ibase_mul[0] + a.ioff[0], ib1 = org[1] * a.ibase_mul[1] + a.ioff[1],
               ib2 = org[2] * a.ibase_mul[2] + a.ioff[2];
-    const int rows_per_sc = a.H[0] * a.H[1];
-    const int nrows = a.nslab * a.cgin * rows_per_sc;
-    for (int row = warp; row < nrows; row += kThreads / 32) {
-      const int sc = row / rows_per_sc, h01 = row - sc * rows_per_sc;
-      const int slab = sc / a.cgin, cg = sc - slab * a.cgin;
-      const int h0 = h01 / a.H[1], h1 = h01 - h0 * a.H[1];
+    const int nrows = a.nslab * a.cgin * a.H[0] * a.H[1];
+    // row = ((slab*cgin + cg)*H0 + h0)*H1 + h1, advanced incrementally (no per-row division)
+    int row = warp;
+    int h1 = row % a.H[1];
+    int pl = row / a.H[1];
+    int h0 = pl % a.H[0];
+    int sc = pl / a.H[0];
+    int cg = sc % a.cgin, slab = sc / a.cgin;
+    while (row < nrows) {
       int bits = slab;  // parity bits, least significant = axis 2 (only axes with par==2 consume a bit)
       const int r2 = a.par[2] == 2 ? (bits & 1) : 0;
       bits >>= (a.par[2] == 2);
@@ -262,20 +280,29 @@ __global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const KArgs a) {
       const __nv_bfloat16* base = (cg < a.cg0) ? a.in0 + ((long long)n * a.cg0 + cg) * ivox * 8
                                                : a.in1 + ((long long)n * a.cg1 + (cg - a.cg0)) * ivox * 8;
       const long long rowoff = ((long long)i0 * a.id[1] + i1) * a.id[2];
-      const uint32_t dst_row = a_base + (uint32_t)(sc * a.P + h01 * a.H[2]) * 16u;
+      const uint32_t dst_row = a_base + (uint32_t)((slab * a.cgin + cg) * a.P + (h0 * a.H[1] + h1) * a.H[2]) * 16u;
       for (int h2 = lane; h2 < a.H[2]; h2 += 32) {
         const int i2 = ib2 + a.imul[2] * h2 + r2;
         const bool ok = ok01 && i2 >= 0 && i2 < a.id[2];
         const __nv_bfloat16* src = ok ? base + (rowoff + i2) * 8 : a.in0;
         cp_async16(dst_row + (uint32_t)h2 * 16u, src, ok ? 16u : 0u);
       }
+      row += kThreads / 32;
+      h1 += kThreads / 32;
+      while (h1 >= a.H[1]) {
+        h1 -= a.H[1];
+        if (++h0 == a.H[0]) {
+          h0 = 0;
+          if (++cg == a.cgin) cg = 0, ++slab;
+        }
+      }
     }
-    // zero the tail the last M tile may read (keeps garbage rows finite; they are discarded anyway)
-    for (int it = a.nslab * a.cgin * a.P + tid; it < a.a_units; it += kThreads)
-      *reinterpret_cast<uint4*>(a_smem + (size_t)it * 16) = make_uint4(0, 0, 0, 0);
     asm volatile("cp.async.wait_all;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core reads
   }
+  // zero the tail the last M tile may read (keeps garbage rows finite; they are discarded anyway)
+  for (int it = a.nslab * a.cgin * a.P + tid; it < a.a_units; it += kThreads)
+    *reinterpret_cast<uint4*>(a_smem + (size_t)it * 16) = make_uint4(0, 0, 0, 0);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core reads
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -285,6 +312,19 @@ __global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const KArgs a) {
   if (warp == 5) {
     // ================= weight producer: cp.async.bulk ring =================
     if (lane == 0) {
+      if (a.use_tma) {
+        // halo brick by TMA: one 4-D box {H2*8 elements, H1, H0, 1 channel group} per group; coordinates may
+        // be negative / past the extent -> hardware zero fill == the conv's zero padding at the window border
+        mbar_expect_tx(ABAR, (uint32_t)(a.cgin * a.box_bytes));
+        const uint32_t a_base = smem_u32(a_smem);
+        const int c0 = (org[2] * a.ibase_mul[2] + a.ioff[2]) * 8, c1 = org[1] * a.ibase_mul[1] + a.ioff[1],
+                  c2 = org[0] * a.ibase_mul[0] + a.ioff[0];
+        for (int cg = 0; cg < a.cgin; ++cg) {
+          const bool first_src = cg < a.cg0;
+          tma_load_4d(a_base + (uint32_t)(cg * a.P) * 16u, first_src ? &tmap0 : &tmap1, c0, c1, c2,
+                      first_src ? n * a.cg0 + cg : n * a.cg1 + (cg - a.cg0), ABAR);
+        }
+      }
       const __nv_bfloat16* wsrc = a.w + (size_t)coblk * a.nblk * N * 16;
       const int total = a.resident ? a.ngroups : a.nchunks * a.ngroups;
       for (int it = 0; it < total; ++it) {
@@ -307,6 +347,7 @@ __global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const KArgs a) {
     const uint32_t a_base16 = smem_u32(a_smem) >> 4;
     const uint32_t w_base16 = smem_u32(w_smem) >> 4;
     const int H12 = a.H[1] * a.H[2];
+    if (a.use_tma) mbar_wait_or_trap(ABAR, 0u, a.error_flag, 5);
     for (int chunk = 0; chunk < a.nchunks; ++chunk) {
       const int buf = a.nbuf == 2 ? (chunk & 1) : 0;
       const int use = a.nbuf == 2 ? (chunk >> 1) : chunk;
@@ -497,8 +538,12 @@ bool tc_supported(const sgm_conv_desc& d) {
   return (d.kernel == 3 || d.kernel == 1) && (d.stride == 1 || d.stride == 2);
 }
 
+struct PlanEntry;
+static void free_plans(void* p);
+
 void tc_free(TcConv* c) {
   if (!c) return;
+  free_plans(c->plan_cache);
   if (c->w) cudaFree(c->w);
   if (c->bias) cudaFree(c->bias);
   delete c;
@@ -543,6 +588,7 @@ int tc_pack(const sgm_conv_desc* m, const sgm_conv_desc* second, int spatial_dim
   *out = nullptr;
   SGM_REQUIRE(m && tc_supported(*m), SGM_ERR_UNSUPPORTED, "conv not supported by the tcgen05 family");
   TcConv* c = new TcConv();
+  c->plan_cache = new std::vector<PlanEntry>();
   const bool tr2 = m->kind == SGM_KIND_CONV_TRANSPOSE && m->stride == 2;
   c->mode = tr2 ? MODE_T2 : (m->stride == 2 ? MODE_S2 : MODE_S1);
   c->flat0 = spatial_dims == 2;
@@ -681,12 +727,69 @@ int tc_pack(const sgm_conv_desc* m, const sgm_conv_desc* second, int spatial_dim
   return SGM_OK;
 }
 
-int tc_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t st) {
-  KArgs a;
+// ---- TMA tensor maps for the halo bricks.  A CG8 tensor [n*cg][D0][D1][D2][8 bf16] is a rank-4 tiled
+// tensor {D2*8, D1, D0, n*cg}; one box = one channel group of the brick {H2*8, H1, H0, 1}.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    if (getenv("SGM_NO_TMA")) return nullptr;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+static bool tma_available() { return encode_fn() != nullptr; }
+
+struct MapKey {
+  const void* ptr;
+  int ncg, d[3], h[3];
+};
+struct MapEntry {
+  MapKey key;
+  CUtensorMap map;
+};
+static std::vector<MapEntry> g_maps;
+
+static int make_brick_map(CUtensorMap* out, const void* ptr, int ncg, const int d[3], const int H[3]) {
+  MapKey key{ptr, ncg, {d[0], d[1], d[2]}, {H[0], H[1], H[2]}};
+  for (auto& e : g_maps)
+    if (memcmp(&e.key, &key, sizeof(key)) == 0) {
+      *out = e.map;
+      return SGM_OK;
+    }
+  const cuuint64_t gdim[4] = {(cuuint64_t)d[2] * 8, (cuuint64_t)d[1], (cuuint64_t)d[0], (cuuint64_t)ncg};
+  const cuuint64_t gstr[3] = {(cuuint64_t)d[2] * 16, (cuuint64_t)d[1] * d[2] * 16, (cuuint64_t)d[0] * d[1] * d[2] * 16};
+  const cuuint32_t box[4] = {(cuuint32_t)H[2] * 8, (cuuint32_t)H[1], (cuuint32_t)H[0], 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = encode_fn()(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for dims (%d,%d,%d) x %d groups, box (%d,%d,%d)", (int)r, d[0],
+              d[1], d[2], ncg, H[0], H[1], H[2]);
+    return SGM_ERR_CUDA;
+  }
+  if (g_maps.size() > 4096) g_maps.clear();
+  g_maps.push_back({key, *out});
+  return SGM_OK;
+}
+
+// Geometry of one launch (tile shape search, TMEM / weight-ring sizing): depends only on the conv and the
+// tensor extents, so it is computed once per (conv, dims, batch) and cached.
+static int tc_plan(const TcConv& c, const TcIO& io, KArgs& a, int& smem_bytes_out) {
   memset(&a, 0, sizeof(a));
   SGM_REQUIRE(io.cg0 + io.cg1 == c.cgin, SGM_ERR_INVALID, "tc_launch: input channel groups %d+%d != %d", io.cg0,
               io.cg1, c.cgin);
-  a.in0 = (const __nv_bfloat16*)io.in0, a.in1 = (const __nv_bfloat16*)io.in1;
   a.cg0 = io.cg0, a.cg1 = io.cg1, a.cgin = c.cgin;
   a.mode = c.mode;
   for (int i = 0; i < 3; ++i) {
@@ -738,14 +841,16 @@ int tc_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t
   static const int cand[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64, 96};
   double best = 1e30;
   int bt[3] = {0, 0, 0};
-  const int fixed_bytes = a.nstages * a.w_stage_bytes + (2 * a.nstages + 4) * 8 + 16 + 256;
+  const int fixed_bytes = a.nstages * a.w_stage_bytes + (2 * a.nstages + 5) * 8 + 16 + 256;
+  a.use_tma = (c.mode != MODE_S2) && tma_available();
   for (int c0 : cand)
     for (int c1 : cand)
       for (int c2 : cand) {
         const int t[3] = {std::min(c0, a.rd[0]), std::min(c1, a.rd[1]), std::min(c2, a.rd[2])};
         const int H[3] = {t[0] + addH[0], t[1] + addH[1], t[2] + addH[2]};
-        const int P = H[0] * H[1] * H[2];
+        const int P = round_up(H[0] * H[1] * H[2], 8);
         if (P > 16383) continue;
+        if (a.use_tma && (H[2] * 8 > 256 || H[1] > 256 || H[0] > 256)) continue;  // TMA box limits
         const int rf = (a.lo[0] * H[1] + a.lo[1]) * H[2] + a.lo[2];
         const int rl = ((a.lo[0] + t[0] - 1) * H[1] + a.lo[1] + t[1] - 1) * H[2] + a.lo[2] + t[2] - 1;
         const int ntl = ceil_div(rl - rf + 1, 128);
@@ -768,7 +873,8 @@ int tc_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t
     a.H[i] = bt[i] + addH[i];
     a.nt[i] = ceil_div(a.rd[i], bt[i]);
   }
-  a.P = a.H[0] * a.H[1] * a.H[2];
+  a.P = round_up(a.H[0] * a.H[1] * a.H[2], 8);  // slab stride (16-byte units), 128-byte aligned
+  a.box_bytes = a.H[0] * a.H[1] * a.H[2] * 16;
   a.row_first = (a.lo[0] * a.H[1] + a.lo[1]) * a.H[2] + a.lo[2];
   const int row_last = ((a.lo[0] + a.t[0] - 1) * a.H[1] + a.lo[1] + a.t[1] - 1) * a.H[2] + a.lo[2] + a.t[2] - 1;
   a.ntiles = ceil_div(row_last - a.row_first + 1, 128);
@@ -781,7 +887,38 @@ int tc_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t
   a.a_units = a.nslab * c.cgin * a.P + 128 + 2 * (a.H[1] * a.H[2] + a.H[2] + 2);
   a.a_units = round_up(a.a_units, 8);
   const int smem_bytes = a.a_units * 16 + fixed_bytes;
+  smem_bytes_out = smem_bytes;
+  return SGM_OK;
+}
 
+struct PlanEntry {
+  int key[8];
+  KArgs args;
+  int smem_bytes;
+};
+
+static void free_plans(void* p) { delete reinterpret_cast<std::vector<PlanEntry>*>(p); }
+
+int tc_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t st) {
+  SGM_REQUIRE(io.cg0 + io.cg1 == c.cgin, SGM_ERR_INVALID, "tc_launch: input channel groups %d+%d != %d", io.cg0,
+              io.cg1, c.cgin);
+  const int key[8] = {io.id[0], io.id[1], io.id[2], io.od[0], io.od[1], io.od[2], io.n, io.cg0};
+  auto* plans = reinterpret_cast<std::vector<PlanEntry>*>(c.plan_cache);
+  const PlanEntry* pe = nullptr;
+  for (auto& e : *plans)
+    if (memcmp(e.key, key, sizeof(key)) == 0) pe = &e;
+  if (!pe) {
+    PlanEntry e;
+    memcpy(e.key, key, sizeof(key));
+    int rc = tc_plan(c, io, e.args, e.smem_bytes);
+    if (rc) return rc;
+    plans->push_back(e);
+    pe = &plans->back();
+  }
+  KArgs a = pe->args;
+  const int smem_bytes = pe->smem_bytes;
+  const int N = c.ncta, nblk = (int)c.blocks.size();
+  a.in0 = (const __nv_bfloat16*)io.in0, a.in1 = (const __nv_bfloat16*)io.in1;
   a.blk_off = c.blk_off;
   a.w = c.w, a.bias = c.bias;
   a.outA = (__nv_bfloat16*)io.outA, a.cgA = io.cgA, a.outB = (__nv_bfloat16*)io.outB, a.cgB = io.cgB;
@@ -799,17 +936,25 @@ int tc_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t
     fprintf(stderr,
             "[tc_launch] mode=%d N=%d nblk=%d ncls=%d cgin=%d rd=(%d,%d,%d) t=(%d,%d,%d) H=(%d,%d,%d) P=%d nslab=%d "
             "row_first=%d ntiles=%d tpc=%d nchunks=%d nbuf=%d cols/buf=%d tmem=%d G=%d ngroups=%d nstages=%d res=%d "
-            "a_units=%d smem=%d grid=(%d,%d,%d)\n",
+            "a_units=%d smem=%d tma=%d grid=(%d,%d,%d)\n",
             a.mode, N, nblk, a.ncls, a.cgin, a.rd[0], a.rd[1], a.rd[2], a.t[0], a.t[1], a.t[2], a.H[0], a.H[1], a.H[2],
             a.P, a.nslab, a.row_first, a.ntiles, a.tpc, a.nchunks, a.nbuf, a.cols_per_buf, a.tmem_cols, a.G, a.ngroups,
-            a.nstages, a.resident, a.a_units, smem_bytes, a.nt[0] * a.nt[1] * a.nt[2], c.ncoblk, io.n);
+            a.nstages, a.resident, a.a_units, smem_bytes, a.use_tma, a.nt[0] * a.nt[1] * a.nt[2], c.ncoblk, io.n);
   static bool attr_set = false;
   if (!attr_set) {
     SGM_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     attr_set = true;
   }
+  CUtensorMap tm0, tm1;
+  memset(&tm0, 0, sizeof(tm0));
+  memset(&tm1, 0, sizeof(tm1));
+  if (a.use_tma) {
+    int rc = make_brick_map(&tm0, io.in0, io.n * io.cg0, io.id, a.H);
+    if (!rc && io.in1) rc = make_brick_map(&tm1, io.in1, io.n * io.cg1, io.id, a.H);
+    if (rc) return rc;
+  }
   dim3 grid(a.nt[0] * a.nt[1] * a.nt[2], c.ncoblk, io.n);
-  tc_conv_kernel<<<grid, kThreads, smem_bytes, st>>>(a);
+  tc_conv_kernel<<<grid, kThreads, smem_bytes, st>>>(a, tm0, tm1);
   SGM_CUDA_CHECK(cudaGetLastError());
   return SGM_OK;
 }

@@ -38,6 +38,7 @@ struct TcConv {
   float alphaA = 0.f;
   int c_real = 0;             // real (unpadded) channels of segment A
   int blk_off = -1;           // slice of the constant K-block bank
+  void* plan_cache = nullptr; // launch geometry per (dims, batch), filled lazily by tc_launch
 };
 
 struct TcIO {
