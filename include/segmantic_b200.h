@@ -146,6 +146,17 @@ SGM_API int64_t sgm_sw_workspace_bytes(const sgm_unet* net, const sgm_sw_cfg* cf
 SGM_API int32_t sgm_sw_finalize(const float* acc_dev, int32_t channels, const sgm_sw_cfg* cfg,
                         float* logits_dev, uint8_t* labels_dev, float* probs_dev, void* stream);
 
+/* The whole inferer in one call with a DEFERRED blend: every window's importance-weighted logits are
+ * stored once in the workspace ([window][C][roi] fp32) and a single streaming kernel then sums, for each
+ * output voxel, its covering windows in MONAI's window order, divides by the count and takes
+ * argmax / softmax.  Bit-identical to sgm_sw_accumulate + sgm_sw_finalize (same fp32 operations in
+ * the same order) without any read-modify-write; needs windows * C * roi voxels * 4 extra workspace
+ * bytes.  Any of logits_dev / labels_dev / probs_dev may be NULL. */
+SGM_API int64_t sgm_sw_predict_workspace_bytes(const sgm_unet* net, const sgm_sw_cfg* cfg);
+SGM_API int32_t sgm_sw_predict(sgm_unet* net, const float* vol_dev, const sgm_sw_cfg* cfg, float* logits_dev,
+                               uint8_t* labels_dev, float* probs_dev, void* workspace_dev,
+                               int64_t workspace_bytes, void* stream);
+
 /* Spacingd / its inverse (seg/monai_unet.py:173-174,615-621): out[c][o] = trilinear(in[c], A*o + t),
  * grid_sample(bilinear, padding border, align_corners False) semantics, float64 arithmetic.
  * xform = row-major 3x4 [A|t] mapping OUTPUT voxel indices to INPUT voxel indices. */

@@ -72,6 +72,9 @@ SIGNATURES = {
     "sgm_sw_accumulate": (C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(SwCfg), C.c_void_p, C.c_void_p,
                                       C.c_int64, C.c_void_p]),
     "sgm_sw_workspace_bytes": (C.c_int64, [C.c_void_p, C.POINTER(SwCfg)]),
+    "sgm_sw_predict_workspace_bytes": (C.c_int64, [C.c_void_p, C.POINTER(SwCfg)]),
+    "sgm_sw_predict": (C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(SwCfg), C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_int64, C.c_void_p]),
     "sgm_sw_finalize": (C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(SwCfg), C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
     "sgm_resample_trilinear": (C.c_int32, [C.c_void_p, _I3, C.c_int32, C.c_void_p, _I3, _D, C.c_void_p]),

@@ -67,6 +67,7 @@ struct ConvArgs {
   const float* imap2;
   float imap_floor;
   int c_real;
+  int pl_weighted;  // OUT_PLANAR: logits pre-multiplied by the importance map (deferred blend)
 };
 
 enum { OUT_CG8 = 0, OUT_BLEND = 1, OUT_PLANAR = 2 };

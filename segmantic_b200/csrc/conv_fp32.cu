@@ -168,6 +168,8 @@ __global__ void __launch_bounds__(128) conv_fp32_kernel(const ConvArgs a) {
       imw = fmaxf(__fmul_rn(__fmul_rn(a.imap0[o0[p]], a.imap1[o1]), a.imap2[o2]), a.imap_floor);
     } else if (OUT_KIND == OUT_PLANAR) {
       pl_off = (long long)n * a.pl_nstride + opos;
+      if (a.pl_weighted)
+        imw = fmaxf(__fmul_rn(__fmul_rn(a.imap0[o0[p]], a.imap1[o1]), a.imap2[o2]), a.imap_floor);
     }
 #pragma unroll
     for (int g = 0; g < CO_T / 8; ++g) {
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(128) conv_fp32_kernel(const ConvArgs a) {
             if (OUT_KIND == OUT_BLEND)
               *dst = __fadd_rn(*dst, __fmul_rn(v[c], imw));  // seg *= w; out += seg (two roundings)
             else
-              *dst = v[c];
+              *dst = a.pl_weighted ? __fmul_rn(v[c], imw) : v[c];
           }
         }
       }

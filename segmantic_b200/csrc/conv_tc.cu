@@ -60,6 +60,8 @@ struct KArgs {
   int segA_cg, actA;
   float alphaA;
   const __nv_bfloat16* res;
+  int res_mode;       // 0 none, 1 global CG8 tensor, 2 identity: centre of the shared-memory brick
+  int pl_weighted;    // OUT_PLANAR: multiply by the window importance map (deferred blend)
   int out_kind;
   float* pl_out;
   long long pl_cstride, pl_nstride;
@@ -75,6 +77,7 @@ struct KArgs {
   int a_units;        // 16-byte units reserved for the A region
   int w_stage_bytes;
   int* error_flag;
+  long long* trace;   // optional (SGM_TRACE): clock64 stamps of CTA 0's phases
 };
 
 // ------------------------------------------------------------------------------------ PTX wrappers
@@ -219,6 +222,9 @@ tc_conv_kernel(const KArgs a, const __grid_constant__ CUtensorMap tmap0, const _
   const int b1 = tile_lin % a.nt[1];
   const int b0 = tile_lin / a.nt[1];
   const int org[3] = {b0 * a.t[0], b1 * a.t[1], b2 * a.t[2]};  // tile origin in row space
+  const bool tr = a.trace != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0;
+#define SGM_TRACE(slot) do { if (tr && lane == 0) a.trace[slot] = clock64(); } while (0)
+  if (warp == 0) SGM_TRACE(0);
 
   uint8_t* a_smem = smem;
   const int a_bytes = a.a_units * 16;
@@ -307,6 +313,7 @@ tc_conv_kernel(const KArgs a, const __grid_constant__ CUtensorMap tmap0, const _
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0) SGM_TRACE(1);
 
   const int N = a.N;
   if (warp == 5) {
@@ -341,180 +348,199 @@ tc_conv_kernel(const KArgs a, const __grid_constant__ CUtensorMap tmap0, const _
       }
     }
   } else if (warp == 4) {
-    // ================= MMA issuer: the whole warp runs the (uniform) loop, one elected lane issues ======
-    // instruction descriptor: D=f32, A=B=bf16, K-major both, N>>3 at [17,23), M>>4 at [24,29)
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
-    const uint32_t a_base16 = smem_u32(a_smem) >> 4;
-    const uint32_t w_base16 = smem_u32(w_smem) >> 4;
-    const int H12 = a.H[1] * a.H[2];
-    if (a.use_tma) mbar_wait_or_trap(ABAR, 0u, a.error_flag, 5);
-    for (int chunk = 0; chunk < a.nchunks; ++chunk) {
-      const int buf = a.nbuf == 2 ? (chunk & 1) : 0;
-      const int use = a.nbuf == 2 ? (chunk >> 1) : chunk;
-      if (use > 0) mbar_wait_or_trap(TEMPTY(buf), (uint32_t)(use - 1) & 1u, a.error_flag, 2);
-      tc_fence_after();
-      const int tiles_here = min(a.tpc, a.ntiles - chunk * a.tpc);
-      for (int g = 0; g < a.ngroups; ++g) {
-        int stage = g;
-        if (!a.resident || chunk == 0) {
-          const int it = a.resident ? g : chunk * a.ngroups + g;
-          stage = it % a.nstages;
-          mbar_wait_or_trap(WFULL(stage), (uint32_t)(it / a.nstages) & 1u, a.error_flag, 3);
-          tc_fence_after();
-        }
-        const int bend = min(a.nblk, (g + 1) * a.G);
-        for (int b = g * a.G; b < bend; ++b) {
-          const uint32_t d = c_blk[a.blk_off + b];
-          const int s0 = (int)(d & 3u) - 1, s1 = (int)((d >> 2) & 3u) - 1, s2 = (int)((d >> 4) & 3u) - 1;
-          const int slab = (d >> 6) & 7u, cls = (d >> 9) & 7u, cgpair = (d >> 16) & 0xffu;
-          const uint32_t acc = ((d >> 12) & 1u) ? 0u : 1u;
-          const int a16 = (slab * a.cgin + cgpair * 2) * a.P + a.row_first + s0 * H12 + s1 * a.H[2] + s2;
-          const uint64_t bdesc =
-              make_desc(w_base16 + (uint32_t)(stage * a.w_stage_bytes + (b - g * a.G) * N * 32) / 16u, (uint32_t)N, 8u);
-          const uint32_t col = tmem_base + (uint32_t)(buf * a.cols_per_buf + cls * N);
-          for (int t = 0; t < tiles_here; ++t) {
-            const uint64_t adesc = make_desc(a_base16 + (uint32_t)(a16 + (chunk * a.tpc + t) * 128), (uint32_t)a.P, 8u);
-            if (elect_one()) tc_mma(col + (uint32_t)(t * a.ncls * N), adesc, bdesc, idesc, acc);
+    // ================= MMA issuer: ONE elected lane runs the whole issue loop ======================
+    // (elect.sync tells the compiler exactly one lane is live, so descriptors move to uniform
+    // registers with plain R2UR -- no per-MMA election / reconvergence and no waterfall loops.)
+    if (elect_one()) {
+      // instruction descriptor: D=f32, A=B=bf16, K-major both, N>>3 at [17,23), M>>4 at [24,29)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t a_base16 = smem_u32(a_smem) >> 4;
+      const uint32_t w_base16 = smem_u32(w_smem) >> 4;
+      const int H12 = a.H[1] * a.H[2];
+      const uint32_t desc_hi = 8u | (1u << 14);                 // SBO = 128 B, version 1
+      const uint32_t a_lbo = ((uint32_t)a.P & 0x3FFFu) << 16;   // next channel group of the brick
+      const uint32_t b_lbo = ((uint32_t)N & 0x3FFFu) << 16;     // next 8 input channels of the filter block
+      const uint32_t tile_cols = (uint32_t)(a.ncls * N);
+      if (a.use_tma) mbar_wait_or_trap(ABAR, 0u, a.error_flag, 5);
+      if (tr) a.trace[2] = clock64();
+      for (int chunk = 0; chunk < a.nchunks; ++chunk) {
+        const int buf = a.nbuf == 2 ? (chunk & 1) : 0;
+        const int use = a.nbuf == 2 ? (chunk >> 1) : chunk;
+        if (use > 0) mbar_wait_or_trap(TEMPTY(buf), (uint32_t)(use - 1) & 1u, a.error_flag, 2);
+        tc_fence_after();
+        const int tiles_here = min(a.tpc, a.ntiles - chunk * a.tpc);
+        for (int g = 0; g < a.ngroups; ++g) {
+          int stage = g;
+          if (!a.resident || chunk == 0) {
+            const int it = a.resident ? g : chunk * a.ngroups + g;
+            stage = it % a.nstages;
+            mbar_wait_or_trap(WFULL(stage), (uint32_t)(it / a.nstages) & 1u, a.error_flag, 3);
+            tc_fence_after();
+            if (tr && chunk == 0 && g == 0) a.trace[3] = clock64();
           }
+          const int bend = min(a.nblk, (g + 1) * a.G);
+          uint32_t b_lo = (w_base16 + (uint32_t)(stage * a.w_stage_bytes) / 16u) | b_lbo;
+          for (int b = g * a.G; b < bend; ++b, b_lo += (uint32_t)(N * 2)) {
+            const uint32_t d = c_blk[a.blk_off + b];
+            const int s0 = (int)(d & 3u) - 1, s1 = (int)((d >> 2) & 3u) - 1, s2 = (int)((d >> 4) & 3u) - 1;
+            const int slab = (d >> 6) & 7u, cls = (d >> 9) & 7u, cgpair = (d >> 16) & 0xffu;
+            const uint32_t acc = ((d >> 12) & 1u) ? 0u : 1u;
+            const int a16 = (slab * a.cgin + cgpair * 2) * a.P + a.row_first + s0 * H12 + s1 * a.H[2] + s2;
+            const uint64_t bdesc = ((uint64_t)desc_hi << 32) | b_lo;
+            uint32_t a_lo = (a_base16 + (uint32_t)(a16 + chunk * a.tpc * 128)) | a_lbo;
+            uint32_t col = tmem_base + (uint32_t)(buf * a.cols_per_buf + cls * N);
+#pragma unroll 4
+            for (int t = 0; t < tiles_here; ++t, a_lo += 128u, col += tile_cols)
+              tc_mma(col, ((uint64_t)desc_hi << 32) | a_lo, bdesc, idesc, acc);
+          }
+          if (!a.resident) tc_commit(WEMPTY(stage));
         }
-        if (!a.resident && elect_one()) tc_commit(WEMPTY(stage));
+        tc_commit(TFULL(buf));
+        if (tr && chunk < 4) a.trace[4 + chunk] = clock64();  // all MMAs of the chunk issued
       }
-      if (elect_one()) tc_commit(TFULL(buf));
-      __syncwarp();
     }
+    __syncwarp();
   } else {
     // ================= epilogue warps 0..3: TMEM lanes 32*warp .. 32*warp+31 =================
+    // Work items = (tile, class, 16-column piece) of the chunk, walked linearly so that the global
+    // residual of item i+1 is in flight while item i is processed.  Identity residuals (up-path
+    // residual units and the head: residual == the conv input) come from the shared-memory brick.
     const long long ovox = (long long)a.od[0] * a.od[1] * a.od[2];
+    const int npiece = N / 16;
     bool ok = true;
     for (int chunk = 0; chunk < a.nchunks && ok; ++chunk) {
       const int buf = a.nbuf == 2 ? (chunk & 1) : 0;
       const int use = a.nbuf == 2 ? (chunk >> 1) : chunk;
       const int tiles_here = min(a.tpc, a.ntiles - chunk * a.tpc);
-      // head (blend) path: the accumulator read-modify-write does not depend on the MMA results, so the
-      // old values of the first tile are fetched BEFORE waiting for the tensor core.
-      float oldv[16];
-      auto row_geom = [&](int t, int& o0, int& o1, int& o2) -> bool {
-        const int p = a.row_first + (chunk * a.tpc + t) * 128 + warp * 32 + lane;
+      const int nitems = tiles_here * a.ncls * npiece;
+      // geometry of an item: validity, output position, brick row
+      auto item_geom = [&](int it, int& t, int& cls, int& piece, int& p, int& o0, int& o1, int& o2) -> bool {
+        piece = it % npiece;
+        const int tc_ = it / npiece;
+        cls = tc_ % a.ncls;
+        t = tc_ / a.ncls;
+        p = a.row_first + (chunk * a.tpc + t) * 128 + warp * 32 + lane;
         const int h2 = p % a.H[2];
         const int h01 = p / a.H[2];
         const int h1 = h01 % a.H[1], h0 = h01 / a.H[1];
-        o0 = org[0] + h0 - a.lo[0], o1 = org[1] + h1 - a.lo[1], o2 = org[2] + h2 - a.lo[2];
-        return h0 >= a.lo[0] && h0 < a.lo[0] + a.t[0] && h1 >= a.lo[1] && h1 < a.lo[1] + a.t[1] &&
-               h2 >= a.lo[2] && h2 < a.lo[2] + a.t[2] && o0 < a.rd[0] && o1 < a.rd[1] && o2 < a.rd[2];
+        const int r0 = org[0] + h0 - a.lo[0], r1 = org[1] + h1 - a.lo[1], r2 = org[2] + h2 - a.lo[2];
+        const bool v = h0 >= a.lo[0] && h0 < a.lo[0] + a.t[0] && h1 >= a.lo[1] && h1 < a.lo[1] + a.t[1] &&
+                       h2 >= a.lo[2] && h2 < a.lo[2] + a.t[2] && r0 < a.rd[0] && r1 < a.rd[1] && r2 < a.rd[2];
+        o0 = r0, o1 = r1, o2 = r2;
+        if (a.mode == MODE_T2) {
+          int bits = cls;
+          o2 = 2 * r2 + (bits & 1);
+          bits >>= 1;
+          o1 = 2 * r1 + (bits & 1);
+          bits >>= 1;
+          o0 = a.par[0] == 2 ? 2 * r0 + (bits & 1) : r0;
+        }
+        return v;
       };
-      auto blend_prefetch = [&](int t) {
-        int o0, o1, o2;
-        const bool v = row_geom(t, o0, o1, o2);
-        const int g0 = a.wo[0] + o0;
-        if (v && g0 >= 0 && g0 < a.ad0) {
-          const long long off = ((long long)g0 * a.ad1 + (a.wo[1] + o1)) * a.ad2 + (a.wo[2] + o2);
-#pragma unroll
-          for (int c = 0; c < 16; ++c)
-            if (c < a.c_real) oldv[c] = __ldcg(a.pl_out + c * a.pl_cstride + off);
+      uint4 nres[2];  // prefetched global residual (two channel groups) of the next item
+      auto res_prefetch = [&](int it) {
+        int t, cls, piece, p, o0, o1, o2;
+        const bool v = item_geom(it, t, cls, piece, p, o0, o1, o2);
+        const int gcg = (coblk * N + piece * 16) >> 3;
+        nres[0] = nres[1] = make_uint4(0, 0, 0, 0);
+        if (v && gcg < a.segA_cg) {
+          const long long opos = ((long long)o0 * a.od[1] + o1) * a.od[2] + o2;
+          nres[0] = __ldg(reinterpret_cast<const uint4*>(a.res + (((long long)n * a.cgA + gcg) * ovox + opos) * 8));
+          nres[1] = __ldg(reinterpret_cast<const uint4*>(a.res + (((long long)n * a.cgA + gcg + 1) * ovox + opos) * 8));
         }
       };
-      const bool blend = a.out_kind == OUT_BLEND && N == 16;
-      if (blend) blend_prefetch(0);
+      if (a.res_mode == 1) res_prefetch(0);
       ok = mbar_wait(TFULL(buf), (uint32_t)use & 1u, a.error_flag, 4);
       if (!ok) break;
       tc_fence_after();
-      for (int t = 0; t < tiles_here; ++t) {
-        int r0, r1, r2;
-        const bool valid = row_geom(t, r0, r1, r2);
-        for (int cls = 0; cls < a.ncls; ++cls) {
-          int o0 = r0, o1 = r1, o2 = r2;
-          if (a.mode == MODE_T2) {
-            int bits = cls;
-            o2 = 2 * r2 + (bits & 1);
-            bits >>= 1;
-            o1 = 2 * r1 + (bits & 1);
-            bits >>= 1;
-            o0 = a.par[0] == 2 ? 2 * r0 + (bits & 1) : r0;
-          }
-          const long long opos = ((long long)o0 * a.od[1] + o1) * a.od[2] + o2;
-          const uint32_t tcol =
-              tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * a.cols_per_buf + (t * a.ncls + cls) * N);
-          for (int piece = 0; piece < N / 16; ++piece) {
-            uint32_t raw[16];
-            tc_ld16(tcol + piece * 16, raw);  // warp-collective: every lane executes it
-            const int cbase = coblk * N + piece * 16;  // fused output channel of raw[0]
-            const int gcg = cbase >> 3;
-            const bool segA = gcg < a.segA_cg;
-            float v[16];
+      if (warp == 0 && chunk < 4) SGM_TRACE(8 + chunk);  // accumulators of the chunk complete
+      for (int it = 0; it < nitems; ++it) {
+        int t, cls, piece, p, o0, o1, o2;
+        const bool valid = item_geom(it, t, cls, piece, p, o0, o1, o2);
+        const long long opos = ((long long)o0 * a.od[1] + o1) * a.od[2] + o2;
+        const uint32_t tcol = tmem_base + ((uint32_t)(warp * 32) << 16) +
+                              (uint32_t)(buf * a.cols_per_buf + (t * a.ncls + cls) * N + piece * 16);
+        uint32_t raw[16];
+        tc_ld16(tcol, raw);  // warp-collective: every lane executes it
+        const uint4 cres0 = nres[0], cres1 = nres[1];
+        if (a.res_mode == 1 && it + 1 < nitems) res_prefetch(it + 1);
+        const int cbase = coblk * N + piece * 16;  // fused output channel of raw[0]
+        const int gcg = cbase >> 3;
+        const bool segA = gcg < a.segA_cg;
+        float v[16];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-              float x = __uint_as_float(raw[c]) + __ldg(a.bias + cbase + c);
-              if (segA && a.actA) x = prelu(x, a.alphaA);
-              v[c] = x;
-            }
-            if (segA) {
-              if (a.res && valid) {
+        for (int c = 0; c < 16; ++c) {
+          float x = __uint_as_float(raw[c]) + __ldg(a.bias + cbase + c);
+          if (segA && a.actA) x = prelu(x, a.alphaA);
+          v[c] = x;
+        }
+        if (!valid) continue;
+        if (segA) {
+          if (a.res_mode == 1) {
+            float r[8];
+            unpack8(cres0, r);
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                  float r[8];
-                  unpack8(__ldg(reinterpret_cast<const uint4*>(
-                              a.res + (((long long)n * a.cgA + gcg + h) * ovox + opos) * 8)),
-                          r);
+            for (int c = 0; c < 8; ++c) v[c] += r[c];
+            unpack8(cres1, r);
 #pragma unroll
-                  for (int c = 0; c < 8; ++c) v[h * 8 + c] += r[c];
-                }
-              }
-              if (a.out_kind == OUT_CG8) {
-                if (valid) {
+            for (int c = 0; c < 8; ++c) v[8 + c] += r[c];
+          } else if (a.res_mode == 2) {  // identity residual: centre of the brick, channel group = gcg
 #pragma unroll
-                  for (int h = 0; h < 2; ++h)
-                    if (gcg + h < a.cgA)
-                      *reinterpret_cast<uint4*>(a.outA + (((long long)n * a.cgA + gcg + h) * ovox + opos) * 8) =
-                          pack8(v + h * 8);
-                }
-              } else if (a.out_kind == OUT_BLEND) {
-                const int g0 = a.wo[0] + o0;
-                const bool pl_ok = valid && g0 >= 0 && g0 < a.ad0;
-                const long long off = ((long long)g0 * a.ad1 + (a.wo[1] + o1)) * a.ad2 + (a.wo[2] + o2);
-                float res_v[16];
-                if (pl_ok) {
-                  const float imw =
-                      fmaxf(__fmul_rn(__fmul_rn(a.imap0[o0], a.imap1[o1]), a.imap2[o2]), a.imap_floor);
-                  if (!blend) {
+            for (int h = 0; h < 2; ++h) {
+              float r[8];
+              unpack8(*reinterpret_cast<const uint4*>(a_smem + ((size_t)(gcg + h) * a.P + p) * 16), r);
 #pragma unroll
-                    for (int c = 0; c < 16; ++c)
-                      if (cbase + c < a.c_real) oldv[c] = __ldcg(a.pl_out + (cbase + c) * a.pl_cstride + off);
-                  }
-#pragma unroll
-                  for (int c = 0; c < 16; ++c)  // seg *= w; out += seg (two roundings, as MONAI)
-                    res_v[c] = __fadd_rn(oldv[c], __fmul_rn(v[c], imw));
-                }
-                // fetch the next tile's accumulator values before storing (keeps ~C loads in flight)
-                if (blend && t + 1 < tiles_here) blend_prefetch(t + 1);
-                if (pl_ok) {
-#pragma unroll
-                  for (int c = 0; c < 16; ++c)
-                    if (cbase + c < a.c_real) __stcg(a.pl_out + (cbase + c) * a.pl_cstride + off, res_v[c]);
-                }
-              } else if (valid) {
-                const long long off = (long long)n * a.pl_nstride + opos;
-#pragma unroll
-                for (int c = 0; c < 16; ++c)
-                  if (cbase + c < a.c_real) a.pl_out[(cbase + c) * a.pl_cstride + off] = v[c];
-              }
-            } else if (valid) {
-              const int bcg = gcg - a.segA_cg;
-#pragma unroll
-              for (int h = 0; h < 2; ++h)
-                if (bcg + h < a.cgB)
-                  *reinterpret_cast<uint4*>(a.outB + (((long long)n * a.cgB + bcg + h) * ovox + opos) * 8) =
-                      pack8(v + h * 8);
+              for (int c = 0; c < 8; ++c) v[h * 8 + c] += r[c];
             }
           }
+          if (a.out_kind == OUT_CG8) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+              if (gcg + h < a.cgA)
+                *reinterpret_cast<uint4*>(a.outA + (((long long)n * a.cgA + gcg + h) * ovox + opos) * 8) =
+                    pack8(v + h * 8);
+          } else if (a.out_kind == OUT_BLEND) {
+            const int g0 = a.wo[0] + o0;
+            if (g0 >= 0 && g0 < a.ad0) {
+              const long long off = ((long long)g0 * a.ad1 + (a.wo[1] + o1)) * a.ad2 + (a.wo[2] + o2);
+              const float imw = fmaxf(__fmul_rn(__fmul_rn(a.imap0[o0], a.imap1[o1]), a.imap2[o2]), a.imap_floor);
+              float oldv[16];
+#pragma unroll
+              for (int c = 0; c < 16; ++c)
+                if (cbase + c < a.c_real) oldv[c] = __ldcg(a.pl_out + (cbase + c) * a.pl_cstride + off);
+#pragma unroll
+              for (int c = 0; c < 16; ++c)  // seg *= w; out += seg (two roundings, as MONAI)
+                if (cbase + c < a.c_real)
+                  __stcg(a.pl_out + (cbase + c) * a.pl_cstride + off, __fadd_rn(oldv[c], __fmul_rn(v[c], imw)));
+            }
+          } else {  // OUT_PLANAR: fp32 logits [n][C][od], optionally pre-multiplied by the importance map
+            float imw = 1.f;
+            if (a.pl_weighted)
+              imw = fmaxf(__fmul_rn(__fmul_rn(a.imap0[o0], a.imap1[o1]), a.imap2[o2]), a.imap_floor);
+            const long long off = (long long)n * a.pl_nstride + opos;
+#pragma unroll
+            for (int c = 0; c < 16; ++c)
+              if (cbase + c < a.c_real)
+                __stcs(a.pl_out + (cbase + c) * a.pl_cstride + off, a.pl_weighted ? __fmul_rn(v[c], imw) : v[c]);
+          }
+        } else {
+          const int bcg = gcg - a.segA_cg;
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            if (bcg + h < a.cgB)
+              *reinterpret_cast<uint4*>(a.outB + (((long long)n * a.cgB + bcg + h) * ovox + opos) * 8) =
+                  pack8(v + h * 8);
         }
       }
       tc_fence_before();
       mbar_arrive(TEMPTY(buf));
+      if (warp == 0 && chunk < 4) SGM_TRACE(12 + chunk);  // epilogue of the chunk done
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (warp == 0) SGM_TRACE(16);
   if (warp == 5) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols)
                  : "memory");
@@ -924,6 +950,9 @@ int tc_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t
   a.outA = (__nv_bfloat16*)io.outA, a.cgA = io.cgA, a.outB = (__nv_bfloat16*)io.outB, a.cgB = io.cgB;
   a.segA_cg = c.segA_cg, a.actA = c.actA, a.alphaA = c.alphaA;
   a.res = (const __nv_bfloat16*)io.res;
+  a.res_mode = 0;
+  if (io.res) a.res_mode = (io.res == io.in0 && c.mode == MODE_S1 && io.in1 == nullptr && io.cgA == c.cgin) ? 2 : 1;
+  a.pl_weighted = io.pl_weighted;
   a.out_kind = io.out_kind, a.pl_out = io.pl_out, a.pl_cstride = io.pl_cstride, a.pl_nstride = io.pl_nstride;
   a.ad0 = io.ad0, a.ad1 = io.ad1, a.ad2 = io.ad2;
   for (int i = 0; i < 3; ++i) a.wo[i] = io.wo[i];
@@ -945,6 +974,13 @@ int tc_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t
     SGM_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     attr_set = true;
   }
+  static const bool trace_on = getenv("SGM_TRACE") != nullptr;
+  static long long* trace_dev = nullptr;
+  if (trace_on) {
+    if (!trace_dev) cudaMalloc(&trace_dev, 32 * sizeof(long long));
+    cudaMemsetAsync(trace_dev, 0, 32 * sizeof(long long), st);
+    a.trace = trace_dev;
+  }
   CUtensorMap tm0, tm1;
   memset(&tm0, 0, sizeof(tm0));
   memset(&tm1, 0, sizeof(tm1));
@@ -956,6 +992,17 @@ int tc_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t
   dim3 grid(a.nt[0] * a.nt[1] * a.nt[2], c.ncoblk, io.n);
   tc_conv_kernel<<<grid, kThreads, smem_bytes, st>>>(a, tm0, tm1);
   SGM_CUDA_CHECK(cudaGetLastError());
+  if (trace_on) {
+    long long t[32];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(t, trace_dev, sizeof(t), cudaMemcpyDeviceToHost);
+    auto d = [&](int i) { return t[i] ? (double)(t[i] - t[0]) : -1.0; };
+    fprintf(stderr,
+            "[trace] mode=%d N=%d nblk=%d grid=%d t=(%d,%d,%d) ntiles=%d nchunks=%d | setup %.0f brick %.0f w0 %.0f | "
+            "issued %.0f %.0f %.0f %.0f | accdone %.0f %.0f %.0f %.0f | epidone %.0f %.0f %.0f %.0f | end %.0f cycles\n",
+            a.mode, N, nblk, grid.x * grid.y * grid.z, a.t[0], a.t[1], a.t[2], a.ntiles, a.nchunks, d(1), d(2), d(3), d(4),
+            d(5), d(6), d(7), d(8), d(9), d(10), d(11), d(12), d(13), d(14), d(15), d(16));
+  }
   return SGM_OK;
 }
 

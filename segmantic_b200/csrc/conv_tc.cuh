@@ -55,6 +55,7 @@ struct TcIO {
   const void* res = nullptr;  // bf16 CG8 residual added to segment A after the activation
   int out_kind = OUT_CG8;     // OUT_CG8 | OUT_BLEND | OUT_PLANAR (segment A only)
   float* pl_out = nullptr;
+  int pl_weighted = 0;        // OUT_PLANAR: logits pre-multiplied by the importance map (deferred blend)
   long long pl_cstride = 0, pl_nstride = 0;
   int ad0 = 0, ad1 = 0, ad2 = 0;
   int wo[3] = {0, 0, 0};

@@ -24,6 +24,8 @@ void set_error(const char* fmt, ...) {
 int launch_finalize(const float* acc, int channels, const sgm_sw_cfg* cfg, const int* starts_dev,
                     const float* imap_dev[3], float* logits, uint8_t* labels, float* probs,
                     cudaStream_t st);
+int launch_gather_blend(const float* wl, int channels, const sgm_sw_cfg* cfg, const int* starts_dev,
+                        const float* imap_dev[3], float* logits, uint8_t* labels, float* probs, cudaStream_t st);
 
 struct PackedConv {
   int kind = SGM_KIND_IDENTITY;
@@ -182,6 +184,7 @@ struct HeadTarget {
   const int* wo_host;  // [n][3] blend origins (host)
   const float* imap[3];
   float floor;
+  int weighted;  // OUT_PLANAR: store logits * importance map (deferred blend)
 };
 
 inline int out_dim(int i, int k, int s, int pad) { return (i + 2 * pad - k) / s + 1; }
@@ -381,7 +384,9 @@ int run_network(sgm_unet* net, const float* vol, long long vol_cstride, int vd1,
       a.ad0 = head.ad0, a.ad1 = head.ad1, a.ad2 = head.ad2;
       a.imap0 = head.imap[0], a.imap1 = head.imap[1], a.imap2 = head.imap[2];
       a.imap_floor = head.floor;
+      a.pl_weighted = head.weighted;
       tc::TcIO io = tc_io(u, nullptr, u.d);
+      io.pl_weighted = head.weighted;
       io.cgA = u.cg;
       io.pl_out = head.out, io.pl_cstride = head.cstride, io.pl_nstride = head.nstride;
       io.ad0 = head.ad0, io.ad1 = head.ad1, io.ad2 = head.ad2;
@@ -662,6 +667,84 @@ extern "C" int32_t sgm_sw_accumulate(sgm_unet* net, const float* vol_dev, const 
     if (rc) return rc;
   }
   return SGM_OK;
+}
+
+// Window list of a schedule restricted to the axis-0 start range of the call, MONAI order.
+static int build_windows(const sgm_sw_cfg* cfg, std::vector<int>& org_vol, std::vector<int>& org_acc) {
+  for (int a0 = cfg->a0_begin; a0 < cfg->a0_end; ++a0) {
+    const int s0 = cfg->starts[0][a0];
+    SGM_REQUIRE(s0 >= cfg->vol_x0 && s0 + cfg->roi[0] <= cfg->vol_x0 + cfg->vol_nx, SGM_ERR_INVALID,
+                "window start %d needs planes outside vol_dev [%d,%d)", s0, cfg->vol_x0, cfg->vol_x0 + cfg->vol_nx);
+    for (int a1 = 0; a1 < cfg->n_starts[1]; ++a1)
+      for (int a2 = 0; a2 < cfg->n_starts[2]; ++a2) {
+        org_vol.push_back(s0 - cfg->vol_x0), org_vol.push_back(cfg->starts[1][a1]), org_vol.push_back(cfg->starts[2][a2]);
+        org_acc.push_back(s0 - cfg->acc_x0), org_acc.push_back(cfg->starts[1][a1]), org_acc.push_back(cfg->starts[2][a2]);
+      }
+  }
+  return SGM_OK;
+}
+
+extern "C" int64_t sgm_sw_predict_workspace_bytes(const sgm_unet* net, const sgm_sw_cfg* cfg) {
+  const int64_t base = sgm_sw_workspace_bytes(net, cfg);
+  if (base < 0) return base;
+  const int64_t nwin = (int64_t)(cfg->a0_end - cfg->a0_begin) * cfg->n_starts[1] * cfg->n_starts[2];
+  const int64_t roivox = (int64_t)cfg->roi[0] * cfg->roi[1] * cfg->roi[2];
+  return base + nwin * net->cout * roivox * 4 + 3 * SGM_MAX_STARTS * 4 + 1024;
+}
+
+extern "C" int32_t sgm_sw_predict(sgm_unet* net, const float* vol_dev, const sgm_sw_cfg* cfg, float* logits_dev,
+                                  uint8_t* labels_dev, float* probs_dev, void* workspace_dev,
+                                  int64_t workspace_bytes, void* stream) {
+  SGM_REQUIRE(net && vol_dev && workspace_dev, SGM_ERR_INVALID, "sgm_sw_predict: null argument");
+  int rc = check_cfg(net, cfg);
+  if (rc) return rc;
+  SGM_REQUIRE(cfg->a0_begin >= 0 && cfg->a0_end <= cfg->n_starts[0] && cfg->a0_begin <= cfg->a0_end,
+              SGM_ERR_INVALID, "bad axis-0 start range");
+  const int64_t need = sgm_sw_predict_workspace_bytes(net, cfg);
+  SGM_REQUIRE(need >= 0 && workspace_bytes >= need, SGM_ERR_WORKSPACE,
+              "workspace too small: need %lld bytes, got %lld", (long long)need, (long long)workspace_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<int> org_vol, org_acc;
+  rc = build_windows(cfg, org_vol, org_acc);
+  if (rc) return rc;
+  const int nwin = (int)(org_vol.size() / 3);
+  net->last_launches = 0;
+  SGM_REQUIRE(nwin > 0, SGM_ERR_INVALID, "sgm_sw_predict: no windows in the axis-0 range");
+  Bump ws{(char*)workspace_dev, workspace_bytes, 0, false};
+  int* org_dev = (int*)ws.take((int64_t)nwin * 3 * sizeof(int));
+  float* imap_dev = (float*)ws.take(3 * 512 * sizeof(float));
+  int* starts_dev = (int*)ws.take(3 * SGM_MAX_STARTS * sizeof(int));
+  const long long roivox = (long long)cfg->roi[0] * cfg->roi[1] * cfg->roi[2];
+  float* wl = (float*)ws.take((int64_t)nwin * net->cout * roivox * 4);
+  SGM_CUDA_CHECK(cudaMemcpyAsync(org_dev, org_vol.data(), org_vol.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  SGM_CUDA_CHECK(cudaMemcpyAsync(starts_dev, cfg->starts, 3 * SGM_MAX_STARTS * sizeof(int), cudaMemcpyHostToDevice, st));
+  for (int a = 0; a < 3; ++a)
+    SGM_CUDA_CHECK(cudaMemcpyAsync(imap_dev + a * 512, cfg->imap[a], cfg->roi[a] * sizeof(float),
+                                   cudaMemcpyHostToDevice, st));
+  const int B = std::max(1, std::min(cfg->sw_batch, nwin));
+  const long long plane = (long long)cfg->dims[1] * cfg->dims[2];
+  HeadTarget head;
+  memset(&head, 0, sizeof(head));
+  head.kind = OUT_PLANAR, head.weighted = 1;
+  head.cstride = roivox, head.nstride = roivox * net->cout;
+  for (int a = 0; a < 3; ++a) head.imap[a] = imap_dev + a * 512;
+  head.floor = cfg->imap_floor;
+  const int64_t ws_mark = ws.off;
+  int64_t launches = 0;
+  for (int w0 = 0; w0 < nwin; w0 += B) {
+    const int nb = std::min(B, nwin - w0);
+    ws.off = ws_mark;
+    head.out = wl + (size_t)w0 * net->cout * roivox;
+    rc = run_network(net, vol_dev, (long long)cfg->vol_nx * plane, cfg->dims[1], cfg->dims[2],
+                     org_dev + (size_t)w0 * 3, nb, cfg->roi, ws, head, st, false);
+    if (rc) return rc;
+    launches += net->last_launches;
+    net->last_launches = 0;
+  }
+  const float* imaps[3] = {imap_dev, imap_dev + 512, imap_dev + 1024};
+  rc = launch_gather_blend(wl, net->cout, cfg, starts_dev, imaps, logits_dev, labels_dev, probs_dev, st);
+  net->last_launches = launches + 1;
+  return rc;
 }
 
 namespace {

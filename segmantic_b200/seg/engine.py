@@ -8,6 +8,7 @@ PyTorch supplies device buffers and the stream only; all arithmetic is in ``libs
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Optional, Sequence, Tuple
 
 import torch
@@ -186,9 +187,29 @@ def _sw_run(net: UNetB200, vol: torch.Tensor, sched: Schedule, sw_batch_size: in
     x0, nx = acc_rng
     plane = (sched.padded_size[1], sched.padded_size[2])
     cfg, keep = _make_cfg(sched, sw_batch_size, a0, vol_rng, (x0, nx))
-    acc = torch.zeros((C_out, nx) + plane, dtype=torch.float32, device=net.device)
+    blend = os.environ.get("SGM_BLEND", "auto")
     with torch.cuda.device(net.device):
         st = _stream_ptr(net.device)
+        need = lib.sgm_sw_predict_workspace_bytes(net._handle, C.byref(cfg))
+        _lib.check(need, "sgm_sw_predict_workspace_bytes")
+        free_b, _total = torch.cuda.mem_get_info(net.device)
+        have = net._ws.numel() if net._ws is not None else 0
+        deferred = blend == "gather" or (blend == "auto" and need <= have + int(free_b * 0.8))
+    if deferred:  # deferred (gather) blend: no read-modify-write, bit-identical result
+        with torch.cuda.device(net.device):
+            ws = net._workspace(need)
+            logits = torch.empty((C_out, nx) + plane, dtype=torch.float32, device=net.device) if return_logits else None
+            labels = torch.empty((nx,) + plane, dtype=torch.uint8, device=net.device) if return_labels else None
+            probs = torch.empty((C_out, nx) + plane, dtype=torch.float32, device=net.device) if return_probs else None
+            _lib.check(lib.sgm_sw_predict(net._handle, vol.data_ptr(), C.byref(cfg),
+                                          logits.data_ptr() if logits is not None else None,
+                                          labels.data_ptr() if labels is not None else None,
+                                          probs.data_ptr() if probs is not None else None,
+                                          ws.data_ptr(), ws.numel(), st), "sgm_sw_predict")
+        del keep
+        return logits, labels, probs
+    acc = torch.zeros((C_out, nx) + plane, dtype=torch.float32, device=net.device)
+    with torch.cuda.device(net.device):
         need = lib.sgm_sw_workspace_bytes(net._handle, C.byref(cfg))
         _lib.check(need, "sgm_sw_workspace_bytes")
         ws = net._workspace(need)
