@@ -392,7 +392,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--sw-batch", type=int, default=4)
+    ap.add_argument("--sw-batch", type=int, default=32)
     ap.add_argument("--cpu-windows", type=int, default=32, help="windows in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-profile", action="store_true")

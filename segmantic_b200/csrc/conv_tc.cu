@@ -211,6 +211,14 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
 __global__ void __launch_bounds__(kThreads, 2)
 tc_conv_kernel(const KArgs a, const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -322,14 +330,29 @@ tc_conv_kernel(const KArgs a, const __grid_constant__ CUtensorMap tmap0, const _
       if (a.use_tma) {
         // halo brick by TMA: one 4-D box {H2*8 elements, H1, H0, 1 channel group} per group; coordinates may
         // be negative / past the extent -> hardware zero fill == the conv's zero padding at the window border
-        mbar_expect_tx(ABAR, (uint32_t)(a.cgin * a.box_bytes));
+        mbar_expect_tx(ABAR, (uint32_t)(a.nslab * a.cgin * a.box_bytes));
         const uint32_t a_base = smem_u32(a_smem);
-        const int c0 = (org[2] * a.ibase_mul[2] + a.ioff[2]) * 8, c1 = org[1] * a.ibase_mul[1] + a.ioff[1],
+        const int c0 = org[2] * a.ibase_mul[2] + a.ioff[2], c1 = org[1] * a.ibase_mul[1] + a.ioff[1],
                   c2 = org[0] * a.ibase_mul[0] + a.ioff[0];
-        for (int cg = 0; cg < a.cgin; ++cg) {
-          const bool first_src = cg < a.cg0;
-          tma_load_4d(a_base + (uint32_t)(cg * a.P) * 16u, first_src ? &tmap0 : &tmap1, c0, c1, c2,
-                      first_src ? n * a.cg0 + cg : n * a.cg1 + (cg - a.cg0), ABAR);
+        if (a.mode == MODE_S2) {
+          // stride 2: one rank-5 box per (parity slab, channel group), element strides 2 along the split axes
+          for (int slab = 0; slab < a.nslab; ++slab) {
+            int bits = slab;
+            const int r2 = a.par[2] == 2 ? (bits & 1) : 0;
+            bits >>= (a.par[2] == 2);
+            const int r1 = a.par[1] == 2 ? (bits & 1) : 0;
+            bits >>= (a.par[1] == 2);
+            const int r0 = a.par[0] == 2 ? (bits & 1) : 0;
+            for (int cg = 0; cg < a.cgin; ++cg)
+              tma_load_5d(a_base + (uint32_t)((slab * a.cgin + cg) * a.P) * 16u, &tmap0, 0, c0 + r2, c1 + r1, c2 + r0,
+                          n * a.cg0 + cg, ABAR);
+          }
+        } else {
+          for (int cg = 0; cg < a.cgin; ++cg) {
+            const bool first_src = cg < a.cg0;
+            tma_load_4d(a_base + (uint32_t)(cg * a.P) * 16u, first_src ? &tmap0 : &tmap1, c0 * 8, c1, c2,
+                        first_src ? n * a.cg0 + cg : n * a.cg1 + (cg - a.cg0), ABAR);
+          }
         }
       }
       const __nv_bfloat16* wsrc = a.w + (size_t)coblk * a.nblk * N * 16;
@@ -408,11 +431,112 @@ tc_conv_kernel(const KArgs a, const __grid_constant__ CUtensorMap tmap0, const _
     const long long ovox = (long long)a.od[0] * a.od[1] * a.od[2];
     const int npiece = N / 16;
     bool ok = true;
+    // Fast path (N == 16, one class, at most 4 tiles per chunk: the 16-channel layers and the head):
+    // all per-tile geometry is computed BEFORE waiting for the tensor core, bias lives in registers.
+    const bool fast = a.ncls == 1 && npiece == 1 && a.out_kind != OUT_BLEND && a.tpc <= 4;
+    float bias_r[16];
+    if (fast) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c) bias_r[c] = __ldg(a.bias + coblk * N + c);
+    }
     for (int chunk = 0; chunk < a.nchunks && ok; ++chunk) {
       const int buf = a.nbuf == 2 ? (chunk & 1) : 0;
       const int use = a.nbuf == 2 ? (chunk >> 1) : chunk;
       const int tiles_here = min(a.tpc, a.ntiles - chunk * a.tpc);
       const int nitems = tiles_here * a.ncls * npiece;
+      if (fast) {
+        int opos_t[4], prow_t[4];
+        float imw_t[4];
+        bool valid_t[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int p = a.row_first + (chunk * a.tpc + t) * 128 + warp * 32 + lane;
+          const int h2 = p % a.H[2];
+          const int h01 = p / a.H[2];
+          const int h1 = h01 % a.H[1], h0 = h01 / a.H[1];
+          const int r0 = org[0] + h0 - a.lo[0], r1 = org[1] + h1 - a.lo[1], r2 = org[2] + h2 - a.lo[2];
+          valid_t[t] = t < tiles_here && h0 >= a.lo[0] && h0 < a.lo[0] + a.t[0] && h1 >= a.lo[1] &&
+                       h1 < a.lo[1] + a.t[1] && h2 >= a.lo[2] && h2 < a.lo[2] + a.t[2] && r0 < a.rd[0] &&
+                       r1 < a.rd[1] && r2 < a.rd[2];
+          opos_t[t] = (r0 * a.od[1] + r1) * a.od[2] + r2;
+          prow_t[t] = p;
+          imw_t[t] = 1.f;
+          if (a.pl_weighted && valid_t[t])
+            imw_t[t] = fmaxf(__fmul_rn(__fmul_rn(a.imap0[r0], a.imap1[r1]), a.imap2[r2]), a.imap_floor);
+        }
+        const int gcg = (coblk * N) >> 3;
+        const bool segA = gcg < a.segA_cg;
+        uint4 nres0 = make_uint4(0, 0, 0, 0), nres1 = nres0;
+        auto fast_res = [&](int t) {
+          if (valid_t[t] && segA) {
+            nres0 = __ldg(reinterpret_cast<const uint4*>(a.res + (((long long)n * a.cgA + gcg) * ovox + opos_t[t]) * 8));
+            nres1 = __ldg(reinterpret_cast<const uint4*>(a.res + (((long long)n * a.cgA + gcg + 1) * ovox + opos_t[t]) * 8));
+          }
+        };
+        if (a.res_mode == 1) fast_res(0);
+        ok = mbar_wait(TFULL(buf), (uint32_t)use & 1u, a.error_flag, 4);
+        if (!ok) break;
+        tc_fence_after();
+        if (warp == 0 && chunk < 4) SGM_TRACE(8 + chunk);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          if (t >= tiles_here) break;
+          uint32_t raw[16];
+          tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * a.cols_per_buf + t * N), raw);
+          const uint4 cres0 = nres0, cres1 = nres1;
+          if (a.res_mode == 1 && t + 1 < tiles_here) fast_res(t + 1);
+          if (!valid_t[t]) continue;
+          float v[16];
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            float x = __uint_as_float(raw[c]) + bias_r[c];
+            if (segA && a.actA) x = prelu(x, a.alphaA);
+            v[c] = x;
+          }
+          if (segA) {
+            if (a.res_mode == 1) {
+              float r[8];
+              unpack8(cres0, r);
+#pragma unroll
+              for (int c = 0; c < 8; ++c) v[c] += r[c];
+              unpack8(cres1, r);
+#pragma unroll
+              for (int c = 0; c < 8; ++c) v[8 + c] += r[c];
+            } else if (a.res_mode == 2) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                float r[8];
+                unpack8(*reinterpret_cast<const uint4*>(a_smem + ((size_t)(gcg + h) * a.P + prow_t[t]) * 16), r);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) v[h * 8 + c] += r[c];
+              }
+            }
+            if (a.out_kind == OUT_CG8) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+                if (gcg + h < a.cgA)
+                  *reinterpret_cast<uint4*>(a.outA + (((long long)n * a.cgA + gcg + h) * ovox + opos_t[t]) * 8) =
+                      pack8(v + h * 8);
+            } else {  // OUT_PLANAR (fp32 logits, optionally importance-weighted)
+              float* dst = a.pl_out + (long long)n * a.pl_nstride + opos_t[t];
+#pragma unroll
+              for (int c = 0; c < 16; ++c)
+                if (c < a.c_real) __stcs(dst + c * a.pl_cstride, a.pl_weighted ? __fmul_rn(v[c], imw_t[t]) : v[c]);
+            }
+          } else {
+            const int bcg = gcg - a.segA_cg;
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+              if (bcg + h < a.cgB)
+                *reinterpret_cast<uint4*>(a.outB + (((long long)n * a.cgB + bcg + h) * ovox + opos_t[t]) * 8) =
+                    pack8(v + h * 8);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(TEMPTY(buf));
+        if (warp == 0 && chunk < 4) SGM_TRACE(12 + chunk);
+        continue;
+      }
       // geometry of an item: validity, output position, brick row
       auto item_geom = [&](int it, int& t, int& cls, int& piece, int& p, int& o0, int& o1, int& o2) -> bool {
         piece = it % npiece;
@@ -778,7 +902,7 @@ static bool tma_available() { return encode_fn() != nullptr; }
 
 struct MapKey {
   const void* ptr;
-  int ncg, d[3], h[3];
+  int ncg, d[3], h[3], par[3];
 };
 struct MapEntry {
   MapKey key;
@@ -786,13 +910,34 @@ struct MapEntry {
 };
 static std::vector<MapEntry> g_maps;
 
-static int make_brick_map(CUtensorMap* out, const void* ptr, int ncg, const int d[3], const int H[3]) {
-  MapKey key{ptr, ncg, {d[0], d[1], d[2]}, {H[0], H[1], H[2]}};
+static int make_brick_map(CUtensorMap* out, const void* ptr, int ncg, const int d[3], const int H[3],
+                          const int* par = nullptr) {
+  MapKey key{ptr, ncg, {d[0], d[1], d[2]}, {H[0], H[1], H[2]}, {par ? par[0] : 0, par ? par[1] : 0, par ? par[2] : 0}};
   for (auto& e : g_maps)
     if (memcmp(&e.key, &key, sizeof(key)) == 0) {
       *out = e.map;
       return SGM_OK;
     }
+  if (par) {
+    // stride-2 parity slab: rank 5 {8 ch, D2, D1, D0, n*cg}; the box walks 2*H voxels with element stride 2
+    const cuuint64_t gdim5[5] = {8, (cuuint64_t)d[2], (cuuint64_t)d[1], (cuuint64_t)d[0], (cuuint64_t)ncg};
+    const cuuint64_t gstr5[4] = {16, (cuuint64_t)d[2] * 16, (cuuint64_t)d[1] * d[2] * 16,
+                                 (cuuint64_t)d[0] * d[1] * d[2] * 16};
+    const cuuint32_t box5[5] = {8, (cuuint32_t)(H[2] * par[2]), (cuuint32_t)(H[1] * par[1]),
+                                (cuuint32_t)(H[0] * par[0]), 1};
+    const cuuint32_t estr5[5] = {1, (cuuint32_t)par[2], (cuuint32_t)par[1], (cuuint32_t)par[0], 1};
+    CUresult r5 = encode_fn()(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), gdim5, gstr5, box5,
+                              estr5, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r5 != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled (strided) failed (%d) for dims (%d,%d,%d), box (%d,%d,%d)", (int)r5, d[0], d[1],
+                d[2], H[0], H[1], H[2]);
+      return SGM_ERR_CUDA;
+    }
+    if (g_maps.size() > 4096) g_maps.clear();
+    g_maps.push_back({key, *out});
+    return SGM_OK;
+  }
   const cuuint64_t gdim[4] = {(cuuint64_t)d[2] * 8, (cuuint64_t)d[1], (cuuint64_t)d[0], (cuuint64_t)ncg};
   const cuuint64_t gstr[3] = {(cuuint64_t)d[2] * 16, (cuuint64_t)d[1] * d[2] * 16, (cuuint64_t)d[0] * d[1] * d[2] * 16};
   const cuuint32_t box[4] = {(cuuint32_t)H[2] * 8, (cuuint32_t)H[1], (cuuint32_t)H[0], 1};
@@ -827,13 +972,14 @@ static int tc_plan(const TcConv& c, const TcIO& io, KArgs& a, int& smem_bytes_ou
   // weight ring
   a.G = std::max(1, std::min(nblk, 16384 / (N * 32)));
   a.ngroups = ceil_div(nblk, a.G);
-  a.nstages = std::min(3, a.ngroups);
+  a.nstages = std::min(a.G * N * 32 <= 8192 ? 6 : 4, a.ngroups);
   a.resident = a.ngroups <= a.nstages;
   a.w_stage_bytes = round_up(a.G * N * 32, 128);
   // TMEM
   int cols_tile = c.ncls * N;
   a.nbuf = cols_tile <= 128 ? 2 : 1;
   a.tpc = std::max(1, (a.nbuf == 2 ? 128 : 256) / cols_tile);
+  if (c.ncls == 1 && N == 16) a.tpc = 4;  // epilogue fast path: 4 tiles per TMEM buffer
   SGM_REQUIRE(cols_tile <= 256, SGM_ERR_UNSUPPORTED, "tc_launch: %d TMEM columns per tile", cols_tile);
 
   // ---- per-axis geometry of the brick
@@ -868,7 +1014,7 @@ static int tc_plan(const TcConv& c, const TcIO& io, KArgs& a, int& smem_bytes_ou
   double best = 1e30;
   int bt[3] = {0, 0, 0};
   const int fixed_bytes = a.nstages * a.w_stage_bytes + (2 * a.nstages + 5) * 8 + 16 + 256;
-  a.use_tma = (c.mode != MODE_S2) && tma_available();
+  a.use_tma = tma_available() && !(c.mode == MODE_S2 && getenv("SGM_NO_TMA_S2"));
   for (int c0 : cand)
     for (int c1 : cand)
       for (int c2 : cand) {
@@ -876,7 +1022,8 @@ static int tc_plan(const TcConv& c, const TcIO& io, KArgs& a, int& smem_bytes_ou
         const int H[3] = {t[0] + addH[0], t[1] + addH[1], t[2] + addH[2]};
         const int P = round_up(H[0] * H[1] * H[2], 8);
         if (P > 16383) continue;
-        if (a.use_tma && (H[2] * 8 > 256 || H[1] > 256 || H[0] > 256)) continue;  // TMA box limits
+        if (a.use_tma && c.mode != MODE_S2 && (H[2] * 8 > 256 || H[1] > 256 || H[0] > 256)) continue;  // TMA box limits
+        if (a.use_tma && c.mode == MODE_S2 && (H[2] * 2 > 256 || H[1] * 2 > 256 || H[0] * 2 > 256)) continue;
         const int rf = (a.lo[0] * H[1] + a.lo[1]) * H[2] + a.lo[2];
         const int rl = ((a.lo[0] + t[0] - 1) * H[1] + a.lo[1] + t[1] - 1) * H[2] + a.lo[2] + t[2] - 1;
         const int ntl = ceil_div(rl - rf + 1, 128);
@@ -985,7 +1132,7 @@ int tc_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t
   memset(&tm0, 0, sizeof(tm0));
   memset(&tm1, 0, sizeof(tm1));
   if (a.use_tma) {
-    int rc = make_brick_map(&tm0, io.in0, io.n * io.cg0, io.id, a.H);
+    int rc = make_brick_map(&tm0, io.in0, io.n * io.cg0, io.id, a.H, c.mode == MODE_S2 ? a.par : nullptr);
     if (!rc && io.in1) rc = make_brick_map(&tm1, io.in1, io.n * io.cg1, io.id, a.H);
     if (rc) return rc;
   }

@@ -18,6 +18,9 @@ from .sliding_window import Schedule, make_schedule
 from .unet_spec import (KIND_IDENTITY, fold_batchnorm, unet_conv_specs)
 
 
+DEVICE_SW_BATCH = 32  # windows per network launch on the device (memory: ~55 MB / window in bf16)
+
+
 def _require_cuda(device) -> torch.device:
     device = torch.device(device)
     if device.type != "cuda":
@@ -186,7 +189,11 @@ def _sw_run(net: UNetB200, vol: torch.Tensor, sched: Schedule, sw_batch_size: in
     C_out = net.out_channels
     x0, nx = acc_rng
     plane = (sched.padded_size[1], sched.padded_size[2])
-    cfg, keep = _make_cfg(sched, sw_batch_size, a0, vol_rng, (x0, nx))
+    # The reference's sw_batch_size (4) only bounds MONAI's activation memory; results do not depend on
+    # it (eval-mode network, windows are independent).  The device path batches more windows per launch
+    # so that the small deep layers fill the 148 SMs (SGM_SW_BATCH overrides).
+    device_batch = max(int(sw_batch_size), int(os.environ.get("SGM_SW_BATCH", DEVICE_SW_BATCH)))
+    cfg, keep = _make_cfg(sched, device_batch, a0, vol_rng, (x0, nx))
     blend = os.environ.get("SGM_BLEND", "auto")
     with torch.cuda.device(net.device):
         st = _stream_ptr(net.device)
