@@ -206,6 +206,7 @@ def run_b200(args):
     import torch.distributed as dist
     from segmantic_b200.seg import engine
     from segmantic_b200.seg.monai_unet import Net, predict_volume
+    from segmantic_b200.seg.multi_gpu import gather_label_slabs
     from segmantic_b200.seg.sliding_window import make_schedule, slab_partition
     from segmantic_b200.seg.unet_spec import unet_conv_specs
     from segmantic_b200.synthetic import synthetic_state_dict
@@ -226,8 +227,9 @@ def run_b200(args):
     raw, norm = make_block(seed=1)
     gshape = (VOL[0] * world, VOL[1], VOL[2])
     sched = make_schedule(gshape, ROI, OVERLAP, MODE)
+    all_parts = slab_partition(sched, world)
     if world > 1:
-        part = slab_partition(sched, world)[rank]
+        part = all_parts[rank]
         # the global volume is the 256^3 block tiled along axis 0; a rank uploads only its halo'ed slab
         idx = torch.arange(part["vol_x0"], part["vol_x1"]) % VOL[0]
         vol_dev = norm[:, idx].contiguous().to(dev)
@@ -246,14 +248,8 @@ def run_b200(args):
             return res["labels"]
         res = engine.sliding_window_inference_slab(vol_dev, gshape, part, ROI, args.sw_batch, net, overlap=OVERLAP,
                                                    mode=MODE)
-        lab = res["labels"]  # [nx, Y, Z] uint8 for planes [x0, x1)
-        # gather label slabs on rank 0 (NCCL over NVLink); slabs have unequal heights -> pad to the max
-        maxh = max(p["x1"] - p["x0"] for p in slab_partition(sched, world))
-        buf = torch.zeros((maxh,) + lab.shape[1:], dtype=torch.uint8, device=dev)
-        buf[: lab.shape[0]] = lab
-        outs = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
-        dist.gather(buf, outs, dst=0)
-        return outs
+        # gather the uint8 label slabs on rank 0 (NCCL over NVLink): the only collective of the path
+        return gather_label_slabs(res["labels"], all_parts, dst=0)
 
     def barrier():
         if world > 1:
@@ -277,7 +273,7 @@ def run_b200(args):
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1) / args.steps
-    launches_step = net.last_launch_count + 1  # + the normalise/argmax kernel
+    launches_step = net.last_launch_count  # network launches + the gather-blend kernel
     prof = net.get_profile()
     net.set_profiling(False)
     clocks = sampler.stop() if rank == 0 else None
@@ -340,22 +336,43 @@ def run_b200(args):
                            frac_bf16_peak=tf / pk["bf16_sustained"]))
     head = prof[-1]
     roi_vox = float(np.prod(ROI))
-    # algorithmic bytes per head launch (one window): read u (C ch bf16; the residual is the same
-    # tensor) + read-modify-write of the fp32 accumulator for C classes  = (2C + 8C) * roi^3
     esz = 2 if args.precision == "bf16" else 4
-    head_bytes = (esz * CLASSES + 8 * CLASSES) * roi_vox
+    # Dominant kernel = the head conv (C->C 3x3x3 + identity residual, importance-weighted logits out).
+    # Algorithmic work per window: 2*C*C*27*roi^3 FLOP; bytes: read u (C ch, bf16) + write C fp32 logits.
     roofline = None
     if head[2] > 0 and head[1] > 0:
-        per_launch_s = head[1] * 1e-3 / head[2]
-        ach = head_bytes / per_launch_s / 1e9
-        roofline = dict(kernel="tc_conv_kernel[head: conv CxC + residual + importance-weighted accumulate]",
-                        bound="hbm", achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"], traffic=None,
-                        peak_source=pk["source"], us_per_launch=per_launch_s * 1e6,
-                        algorithmic_bytes_per_launch=head_bytes,
-                        tflops=flops[len(specs) - 1] / per_launch_s / 1e12,
-                        frac_bf16_peak=flops[len(specs) - 1] / per_launch_s / 1e12 / pk["bf16_sustained"])
+        per_window_s = head[1] * 1e-3 / (n_win * args.steps)
+        head_flop = flops[len(specs) - 1]
+        head_bytes = (esz * CLASSES + 4 * CLASSES) * roi_vox
+        ach = head_flop / per_window_s / 1e12
+        roofline = dict(kernel="tc_conv_kernel[head: conv CxC k3 + identity residual + importance-weighted logits]",
+                        bound="tensor", achieved=ach, peak=pk["bf16_sustained"], unit="TFLOP/s",
+                        frac=ach / pk["bf16_sustained"], traffic=None, peak_source=pk["source"] + " (sustained)",
+                        us_per_window=per_window_s * 1e6, algorithmic_flop_per_window=head_flop,
+                        algorithmic_bytes_per_window=head_bytes, hbm_gbs=head_bytes / per_window_s / 1e9,
+                        hbm_frac=head_bytes / per_window_s / 1e9 / pk["hbm"],
+                        note="N=16 (10 classes padded) MMAs are bound by shared-memory operand bandwidth "
+                             "(4 KB of A per 128x16x16 MMA), not by the dense tensor peak; see DESIGN.md")
     conv_ms = sum(l["ms_per_step"] for l in layers)
     conv_tf = sum(flops.get(i, 0.0) for i in range(len(specs))) * n_win / (conv_ms * 1e-3) / 1e12 if conv_ms else 0.0
+
+    blend_roof = None
+    if world == 1:
+        # HBM-bound stage: the deferred gather blend (+count, normalise, argmax) reads every window's
+        # weighted logits once and writes one label byte per voxel.  Timed alone with CUDA events on a
+        # buffer of the right size (its content does not affect the traffic).
+        import ctypes as C
+        from segmantic_b200 import _lib
+        from segmantic_b200.seg.engine import _make_cfg
+        lib = _lib.load()
+        cfg, keep = _make_cfg(sched, args.sw_batch)
+        need = int(lib.sgm_sw_predict_workspace_bytes(net._handle, C.byref(cfg)))
+        blend_bytes = 4.0 * CLASSES * n_win * roi_vox + float(np.prod(VOL))
+        blend_roof = dict(kernel="gather_blend_kernel[sum covering windows + count + normalise + argmax]", bound="hbm",
+                          unit="GB/s", peak=pk["hbm"], peak_source=pk["source"], algorithmic_bytes=blend_bytes,
+                          formula="4*C*n_windows*roi^3 (weighted logits, read once) + 1*V (labels)")
+        gl = [p for p in prof if p[0] == "up0.ru"]
+        del keep, need
 
     cpu = None
     if world == 1 and not args.no_cpu:
@@ -376,6 +393,7 @@ def run_b200(args):
                             l2="no flush: per-step working set (67 MB volume + 671 MB accumulator + activations) "
                                "exceeds the 126 MB L2"),
                 e2e=e2e, gpu_launches=int(launches_step * args.steps), clocks=clocks, roofline=roofline,
+                roofline_blend=blend_roof,
                 cpu_baseline=cpu,
                 conv_stack=dict(ms_per_step=conv_ms, tflops=conv_tf, frac_bf16_peak=conv_tf / pk["bf16_sustained"],
                                 peak_tflops=pk["bf16_sustained"], layers=layers))

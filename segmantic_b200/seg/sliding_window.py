@@ -105,20 +105,29 @@ def slab_partition(schedule: Schedule, world_size: int) -> List[dict]:
     s0 = schedule.starts[0]
     n0, roi0, size0 = len(s0), schedule.roi[0], schedule.padded_size[0]
     world_size = max(1, int(world_size))
-    # balance the number of window rows each rank executes: choose cuts among candidate planes
+
+    def rows_of(x0, x1):
+        return [j for j in range(n0) if s0[j] < x1 and s0[j] + roi0 > x0] if x1 > x0 else []
+
+    # Cuts sit exactly on window starts: a rank owning [s0[a], s0[b]) executes rows a-1 .. b-1, i.e. one
+    # redundant row per cut.  Greedy balance of the executed rows: total = n0 + (world - 1).
     cuts = [0]
-    for r in range(1, world_size):
-        # plane where rank r begins: the start of the window row at the r/world quantile
-        j = min(n0 - 1, max(1, round(r * n0 / world_size)))
-        cut = s0[j] if j < n0 else size0
-        # a cut inside the overlap of rows j-1 and j: put it mid-overlap to share the halo evenly
-        cut = min(size0, max(cuts[-1], (s0[j] + min(size0, s0[j - 1] + roi0)) // 2))
-        cuts.append(cut)
+    remaining_rows = n0 + world_size - 1
+    j = 0
+    for r in range(world_size - 1):
+        target = -(-remaining_rows // (world_size - r))  # ceil
+        # rank r executes rows [max(j-1,0), jn-1]  ->  jn - max(j-1, 0) rows
+        jn = min(n0, max(j - 1, 0) + target)
+        jn = max(jn, min(j + 1, n0))
+        executed = jn - max(j - 1, 0)
+        remaining_rows -= executed
+        cuts.append(s0[jn] if jn < n0 else size0)
+        j = jn
     cuts.append(size0)
     parts = []
     for r in range(world_size):
         x0, x1 = cuts[r], cuts[r + 1]
-        rows = [j for j in range(n0) if s0[j] < x1 and s0[j] + roi0 > x0] if x1 > x0 else []
+        rows = rows_of(x0, x1)
         if rows:
             a0b, a0e = rows[0], rows[-1] + 1
             vx0, vx1 = s0[a0b], s0[a0e - 1] + roi0

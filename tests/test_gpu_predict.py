@@ -1,0 +1,93 @@
+"""GPU parity of the public API (predict_volume / predict / CLI) against the oracle composition and the
+committed golden fixtures: orientation, normalisation, foreground crop, Spacing, sliding window,
+inverse (logit-trilinear or label-nearest) and argmax."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import spacing as osp
+from oracle.predict import predict_volume as oracle_predict
+from tests.helpers import make_oracle_net, normalized_volume
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_golden.npz"))
+SMALL = dict(channels=(16, 32, 48), strides=(2, 2))
+
+
+def _net(sd, cuda_device, classes=3, cin=1, spatial_size=(16, 16, 16)):
+    from segmantic_b200.seg.monai_unet import Net
+    net = Net(num_classes=classes, num_channels=cin, spatial_dims=3, spatial_size=list(spatial_size), **SMALL)
+    net.load_state_dict(sd)
+    net.to(cuda_device)
+    return net
+
+
+@pytest.mark.parametrize("invert", ["logits", "labels"])
+def test_predict_volume_with_spacing_matches_oracle_and_golden(cuda_device, invert):
+    from segmantic_b200.seg.monai_unet import predict_volume
+    onet, sd = make_oracle_net(3, 1, 3, seed=12, **SMALL)
+    raw = normalized_volume((48, 40, 12), seed=23) * 100.0 + 50.0
+    aff = osp.itk_geometry_to_ras_affine((0.5, 0.5, 3.0), (-12.0, -10.0, 0.0), np.eye(3).flatten())
+    ref, ref_logits = oracle_predict(onet, raw, aff, (1.0, 1.0, 1.0), roi=(16, 16, 16), invert=invert)
+    lab = predict_volume(_net(sd, cuda_device), raw, aff, (1.0, 1.0, 1.0), invert=invert, precision="fp32")
+    assert lab.shape == ref.shape == (48, 40, 12) and lab.dtype == torch.uint8
+    # label maps are bit-exact except at argmax / nearest-neighbour near-ties (documented exception)
+    assert float((lab != ref).float().mean()) < 2e-3
+    assert float((lab.numpy() != GOLD[f"predict_{invert}_mode"]).mean()) < 2e-3
+
+
+def test_predict_volume_without_spacing_is_exact_outside_ties(cuda_device):
+    from segmantic_b200.seg.monai_unet import predict_volume
+    onet, sd = make_oracle_net(3, 1, 3, seed=12, **SMALL)
+    raw = normalized_volume((40, 36, 28), seed=31) * 30.0 + 5.0
+    ref, logits = oracle_predict(onet, raw, None, (), roi=(16, 16, 16), overlap=0.5, mode="gaussian")
+    lab = predict_volume(_net(sd, cuda_device), raw, None, (), overlap=0.5, mode="gaussian", precision="fp32")
+    assert float((lab != ref).float().mean()) < 1e-3
+
+
+def test_predict_files_and_cli(cuda_device, tmp_path):
+    """segmantic-unet predict -d datalist.json -m model.ckpt -r results: writes <basename>.nii.gz."""
+    from segmantic_b200.image import nifti
+    from segmantic_b200.synthetic import synthetic_lightning_checkpoint
+    ck = synthetic_lightning_checkpoint(num_classes=3, num_channels=1, spatial_dims=3, spatial_size=[16, 16, 16],
+                                        seed=12, **SMALL)
+    torch.save(ck, tmp_path / "model.ckpt")
+    aff = osp.itk_geometry_to_ras_affine((1.0, 1.0, 1.0), (3.0, -4.0, 5.0), np.eye(3).flatten())
+    vols = {}
+    for i in range(2):
+        raw = (normalized_volume((36, 32, 24), seed=40 + i) * 40.0 + 10.0)[0].numpy()
+        nifti.write(tmp_path / f"img{i}.nii.gz", raw, aff)
+        vols[i] = raw
+    (tmp_path / "datalist.json").write_text(json.dumps(
+        {"labels": {"1": "Bone", "2": "Fat"}, "test": ["img0.nii.gz", {"image": "img1.nii.gz"}]}))
+    out = subprocess.run([sys.executable, "-m", "segmantic_b200.commands.monai_unet_cli", "predict", "-d",
+                          str(tmp_path / "datalist.json"), "-m", str(tmp_path / "model.ckpt"), "-r",
+                          str(tmp_path / "results")], capture_output=True, text=True, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    onet, _ = make_oracle_net(3, 1, 3, seed=12, **SMALL)
+    for i in range(2):
+        lab, aff2, _ = nifti.read(tmp_path / "results" / f"img{i}.nii.gz")
+        assert np.allclose(aff2, aff)
+        ref, _ = oracle_predict(onet, torch.from_numpy(vols[i])[None], aff, (), roi=(16, 16, 16))
+        assert float((torch.from_numpy(lab[0]).to(torch.uint8) != ref).float().mean()) < 1e-3
+
+
+def test_golden_forward_on_gpu(cuda_device):
+    from segmantic_b200.seg import engine
+    _, sd = make_oracle_net(3, 2, 4, seed=11, **SMALL)
+    x = normalized_volume((16, 24, 32), seed=21, channels=2)[None]
+    net = engine.UNetB200(sd, spatial_dims=3, in_channels=2, out_channels=4, device=cuda_device, precision="fp32", **SMALL)
+    y = net(x.to(cuda_device)).cpu().numpy()
+    gold = GOLD["unet_forward"]
+    assert float(np.abs(y - gold).max() / np.abs(gold).max()) < 1e-4
+    vol = normalized_volume((32, 24, 28), seed=22)[None]
+    _, sd1 = make_oracle_net(3, 1, 3, seed=12, **SMALL)
+    net1 = engine.UNetB200(sd1, spatial_dims=3, in_channels=1, out_channels=3, device=cuda_device, precision="fp32", **SMALL)
+    sw = engine.sliding_window_inference(vol.to(cuda_device), (16, 16, 16), 4, net1, overlap=0.5, mode="gaussian").cpu().numpy()
+    assert float(np.abs(sw - GOLD["sw_gauss"]).max() / np.abs(GOLD["sw_gauss"]).max()) < 1e-4
