@@ -325,6 +325,8 @@ def run_b200(args):
     flops = per_window_layer_flops(specs, ROI)
     layers = []
     tot_ms = sum(p[1] for p in prof) or 1.0
+    blend_prof = prof[-1]
+    prof = prof[:-1]
     for i, (role, pms, cnt) in enumerate(prof):
         if cnt == 0:
             continue
@@ -360,19 +362,15 @@ def run_b200(args):
     if world == 1:
         # HBM-bound stage: the deferred gather blend (+count, normalise, argmax) reads every window's
         # weighted logits once and writes one label byte per voxel.  Timed alone with CUDA events on a
-        # buffer of the right size (its content does not affect the traffic).
-        import ctypes as C
-        from segmantic_b200 import _lib
-        from segmantic_b200.seg.engine import _make_cfg
-        lib = _lib.load()
-        cfg, keep = _make_cfg(sched, args.sw_batch)
-        need = int(lib.sgm_sw_predict_workspace_bytes(net._handle, C.byref(cfg)))
+        # (measured by the library's CUDA-event pair around the launch, inside the timed region).
         blend_bytes = 4.0 * CLASSES * n_win * roi_vox + float(np.prod(VOL))
-        blend_roof = dict(kernel="gather_blend_kernel[sum covering windows + count + normalise + argmax]", bound="hbm",
-                          unit="GB/s", peak=pk["hbm"], peak_source=pk["source"], algorithmic_bytes=blend_bytes,
-                          formula="4*C*n_windows*roi^3 (weighted logits, read once) + 1*V (labels)")
-        gl = [p for p in prof if p[0] == "up0.ru"]
-        del keep, need
+        if blend_prof[2] > 0 and blend_prof[1] > 0:
+            t = blend_prof[1] * 1e-3 / blend_prof[2]
+            blend_roof = dict(kernel="gather_blend_kernel[sum covering windows + count + normalise + argmax]",
+                              bound="hbm", achieved=blend_bytes / t / 1e9, peak=pk["hbm"], unit="GB/s",
+                              frac=blend_bytes / t / 1e9 / pk["hbm"], traffic=None, peak_source=pk["source"],
+                              ms_per_launch=t * 1e3, algorithmic_bytes_per_launch=blend_bytes,
+                              formula="4*C*n_windows*roi^3 (weighted logits read once) + 1*V (labels written)")
 
     cpu = None
     if world == 1 and not args.no_cpu:

@@ -128,7 +128,8 @@ SGM_API int32_t sgm_debug_conv(sgm_unet* net, int32_t conv_index, int32_t use_tc
                                int32_t out_dims[3], void* stream);
 /* Per-convolution device timing: while on, every conv launch is bracketed by a CUDA-event pair on the
  * launching stream.  sgm_unet_get_profile synchronises, returns the accumulated milliseconds and launch
- * counts per convolution (canonical order, n = n_convs) and resets the counters. */
+ * counts per convolution (canonical order) plus one last slot for the gather-blend kernel
+ * (n = n_convs + 1) and resets the counters. */
 SGM_API int32_t sgm_unet_set_profiling(sgm_unet* net, int32_t on);
 SGM_API int32_t sgm_unet_get_profile(sgm_unet* net, double* ms, int64_t* launches, int32_t n, void* stream);
 /* Number of kernel launches the last forward / sw_accumulate on this handle enqueued. */

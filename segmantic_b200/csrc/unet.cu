@@ -742,7 +742,16 @@ extern "C" int32_t sgm_sw_predict(sgm_unet* net, const float* vol_dev, const sgm
     net->last_launches = 0;
   }
   const float* imaps[3] = {imap_dev, imap_dev + 512, imap_dev + 1024};
+  cudaEvent_t pe = nullptr;
+  if (net->profiling) {  // the blend kernel is profile slot n_convs
+    sgm_unet::ProfEv e;
+    e.a = net->ev_get(), e.b = net->ev_get(), e.conv = (int)net->convs.size();
+    cudaEventRecord(e.a, st);
+    pe = e.b;
+    net->prof_pending.push_back(e);
+  }
   rc = launch_gather_blend(wl, net->cout, cfg, starts_dev, imaps, logits_dev, labels_dev, probs_dev, st);
+  if (pe) cudaEventRecord(pe, st);
   net->last_launches = launches + 1;
   return rc;
 }
@@ -832,8 +841,9 @@ extern "C" int32_t sgm_unet_set_profiling(sgm_unet* net, int32_t on) {
 }
 
 extern "C" int32_t sgm_unet_get_profile(sgm_unet* net, double* ms, int64_t* launches, int32_t n, void* stream) {
-  SGM_REQUIRE(net && ms && launches && n == (int)net->convs.size(), SGM_ERR_INVALID,
-              "sgm_unet_get_profile: expected arrays of %d entries", net ? (int)net->convs.size() : 0);
+  SGM_REQUIRE(net && ms && launches && n == (int)net->convs.size() + 1, SGM_ERR_INVALID,
+              "sgm_unet_get_profile: expected arrays of %d entries (n_convs + 1: the last is the blend kernel)",
+              net ? (int)net->convs.size() + 1 : 0);
   SGM_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
   net->prof_ms.resize(n, 0.0);
   net->prof_n.resize(n, 0);

@@ -149,13 +149,14 @@ class UNetB200:
     def get_profile(self):
         """[(role, ms, launches)] per convolution since the last call (device time, CUDA events)."""
         specs = unet_conv_specs(self.in_channels, self.out_channels, self.channels, self.strides)
-        n = len(specs)
+        n = len(specs) + 1  # + the gather-blend kernel
         ms = (C.c_double * n)()
         cnt = (C.c_int64 * n)()
         with torch.cuda.device(self.device):
             _lib.check(self._lib.sgm_unet_get_profile(self._handle, ms, cnt, n, _stream_ptr(self.device)),
                        "sgm_unet_get_profile")
-        return [(specs[i].role, float(ms[i]), int(cnt[i])) for i in range(n)]
+        roles = [sp.role for sp in specs] + ["gather_blend"]
+        return [(roles[i], float(ms[i]), int(cnt[i])) for i in range(n)]
 
 
 def _make_cfg(sched: Schedule, sw_batch: int, a0=None, vol=None, acc=None):
