@@ -183,7 +183,8 @@ def predict_volume(net: Net, image: torch.Tensor, affine: Optional[np.ndarray] =
         if record is not None:  # nearest-neighbour back-resample of the label map (north-star stage 4)
             lab = _nearest_back(lab, record)
     else:
-        lab = T.resample_index_affine_argmax(res["logits"][0], T.spacing_inverse_xform(record), record["src_shape"])
+        logits = res if isinstance(res, torch.Tensor) else res["logits"]
+        lab = T.resample_index_affine_argmax(logits[0], T.spacing_inverse_xform(record), record["src_shape"])
     if tuple(lab.shape) != oriented_shape:  # inverse CropForeground: zero padding -> label 0
         full = torch.zeros(oriented_shape, dtype=torch.uint8, device=dev)
         full[lo[0]:lo[0] + cropped_shape[0], lo[1]:lo[1] + cropped_shape[1], lo[2]:lo[2] + cropped_shape[2]] = lab

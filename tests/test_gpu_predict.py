@@ -58,6 +58,9 @@ def test_predict_files_and_cli(cuda_device, tmp_path):
     ck = synthetic_lightning_checkpoint(num_classes=3, num_channels=1, spatial_dims=3, spatial_size=[16, 16, 16],
                                         seed=12, **SMALL)
     torch.save(ck, tmp_path / "model.ckpt")
+    # predict() overrides the saved channels/strides with its own defaults (reference behaviour,
+    # monai_unet.py:571-573); a non-default architecture goes through the legacy json sidecar (:564-569)
+    (tmp_path / "model.json").write_text(json.dumps({"channels": [16, 32, 48], "strides": [2, 2]}))
     aff = osp.itk_geometry_to_ras_affine((1.0, 1.0, 1.0), (3.0, -4.0, 5.0), np.eye(3).flatten())
     vols = {}
     for i in range(2):
