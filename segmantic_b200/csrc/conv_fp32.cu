@@ -317,6 +317,7 @@ __global__ void __launch_bounds__(128) convT_fp32_kernel(const ConvArgs a) {
 // too small for the tensor cores; this is a CUDA-core FFMA kernel: one output voxel per thread (lanes
 // along d2), STEM_CO fused output channels per thread, weights broadcast from shared memory.
 constexpr int STEM_CO = 32;
+constexpr int STEM_PT = 2;
 
 struct StemArgs {
   const float* vol;
@@ -347,55 +348,70 @@ __global__ void __launch_bounds__(128) stem_kernel(const StemArgs a) {
   const int b2 = tile % nt2;
   tile /= nt2;
   const int b1 = tile % nt1;
-  const int o0 = tile / nt1;
+  const int o0b = (tile / nt1) * STEM_PT;  // STEM_PT output planes per thread: weights are read once for both
   const int o2 = b2 * 32 + (threadIdx.x & 31), o1 = b1 * 4 + (threadIdx.x >> 5);
   if (o1 >= a.od[1] || o2 >= a.od[2]) return;
   const int w0 = a.win_origin[n * 3 + 0], w1 = a.win_origin[n * 3 + 1], w2 = a.win_origin[n * 3 + 2];
-  float acc[STEM_CO];
+  float acc[STEM_PT][STEM_CO];
 #pragma unroll
-  for (int c = 0; c < STEM_CO; ++c) acc[c] = 0.f;
+  for (int p = 0; p < STEM_PT; ++p)
+#pragma unroll
+    for (int c = 0; c < STEM_CO; ++c) acc[p][c] = 0.f;
   int tap = 0;
   for (int k0 = 0; k0 < a.k[0]; ++k0) {
-    const int i0 = o0 * a.s[0] + k0 - a.pad[0];
     for (int k1 = 0; k1 < a.k[1]; ++k1) {
       const int i1 = o1 * a.s[1] + k1 - a.pad[1];
       for (int k2 = 0; k2 < a.k[2]; ++k2, ++tap) {
         const int i2 = o2 * a.s[2] + k2 - a.pad[2];
-        const bool ok = i0 >= 0 && i0 < a.id[0] && i1 >= 0 && i1 < a.id[1] && i2 >= 0 && i2 < a.id[2];
-        const long long off = ((long long)(w0 + i0) * a.vd1 + (w1 + i1)) * a.vd2 + (w2 + i2);
+        const bool ok12 = i1 >= 0 && i1 < a.id[1] && i2 >= 0 && i2 < a.id[2];
         for (int ci = 0; ci < a.cin; ++ci) {
-          const float x = ok ? __ldg(a.vol + ci * a.vol_cstride + off) : 0.f;
+          float x[STEM_PT];
+#pragma unroll
+          for (int p = 0; p < STEM_PT; ++p) {
+            const int i0 = (o0b + p) * a.s[0] + k0 - a.pad[0];
+            const bool ok = ok12 && i0 >= 0 && i0 < a.id[0];
+            const long long off = ((long long)(w0 + i0) * a.vd1 + (w1 + i1)) * a.vd2 + (w2 + i2);
+            x[p] = ok ? __ldg(a.vol + ci * a.vol_cstride + off) : 0.f;
+          }
           const float4* wr = reinterpret_cast<const float4*>(wsm + (tap * a.cin + ci) * STEM_CO);
 #pragma unroll
           for (int c4 = 0; c4 < STEM_CO / 4; ++c4) {
             const float4 w = wr[c4];
-            acc[c4 * 4 + 0] = fmaf(x, w.x, acc[c4 * 4 + 0]);
-            acc[c4 * 4 + 1] = fmaf(x, w.y, acc[c4 * 4 + 1]);
-            acc[c4 * 4 + 2] = fmaf(x, w.z, acc[c4 * 4 + 2]);
-            acc[c4 * 4 + 3] = fmaf(x, w.w, acc[c4 * 4 + 3]);
+#pragma unroll
+            for (int p = 0; p < STEM_PT; ++p) {
+              acc[p][c4 * 4 + 0] = fmaf(x[p], w.x, acc[p][c4 * 4 + 0]);
+              acc[p][c4 * 4 + 1] = fmaf(x[p], w.y, acc[p][c4 * 4 + 1]);
+              acc[p][c4 * 4 + 2] = fmaf(x[p], w.z, acc[p][c4 * 4 + 2]);
+              acc[p][c4 * 4 + 3] = fmaf(x[p], w.w, acc[p][c4 * 4 + 3]);
+            }
           }
         }
       }
     }
   }
   const long long ovox = (long long)a.od[0] * a.od[1] * a.od[2];
-  const long long opos = ((long long)o0 * a.od[1] + o1) * a.od[2] + o2;
 #pragma unroll
-  for (int g = 0; g < STEM_CO / 8; ++g) {
-    const int fcg = coblk * (STEM_CO / 8) + g;  // fused channel group
-    if (fcg >= a.cgA + a.cgB) continue;
-    const bool isA = fcg < a.cgA;
-    float v[8];
+  for (int p = 0; p < STEM_PT; ++p) {
+    const int o0 = o0b + p;
+    if (o0 >= a.od[0]) continue;
+    const long long opos = ((long long)o0 * a.od[1] + o1) * a.od[2] + o2;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      float t = acc[g * 8 + c] + __ldg(a.bias + fcg * 8 + c);
-      if (isA && a.actA) t = prelu(t, a.alphaA);
-      v[c] = t;
+    for (int g = 0; g < STEM_CO / 8; ++g) {
+      const int fcg = coblk * (STEM_CO / 8) + g;  // fused channel group
+      if (fcg >= a.cgA + a.cgB) continue;
+      const bool isA = fcg < a.cgA;
+      float v[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float t = acc[p][g * 8 + c] + __ldg(a.bias + fcg * 8 + c);
+        if (isA && a.actA) t = prelu(t, a.alphaA);
+        v[c] = t;
+      }
+      if (isA)
+        store8(reinterpret_cast<T*>(a.outA) + (((long long)n * a.cgA + fcg) * ovox + opos) * 8, v);
+      else
+        store8(reinterpret_cast<T*>(a.outB) + (((long long)n * a.cgB + (fcg - a.cgA)) * ovox + opos) * 8, v);
     }
-    if (isA)
-      store8(reinterpret_cast<T*>(a.outA) + (((long long)n * a.cgA + fcg) * ovox + opos) * 8, v);
-    else
-      store8(reinterpret_cast<T*>(a.outB) + (((long long)n * a.cgB + (fcg - a.cgA)) * ovox + opos) * 8, v);
   }
 }
 
@@ -413,7 +429,7 @@ int launch_stem(const ConvArgs& a, int cgA, int cgB, void* outA, void* outB, boo
   const int ntaps = a.k[0] * a.k[1] * a.k[2];
   const size_t smem = (size_t)ntaps * a.cin_real * STEM_CO * sizeof(float);
   SGM_REQUIRE(smem <= 48 * 1024, SGM_ERR_UNSUPPORTED, "stem: %d input channels need %zu B of shared memory", a.cin_real, smem);
-  dim3 grid(ceil_div(a.od[2], 32) * ceil_div(a.od[1], 4) * a.od[0], a.n, ceil_div((cgA + cgB) * 8, STEM_CO));
+  dim3 grid(ceil_div(a.od[2], 32) * ceil_div(a.od[1], 4) * ceil_div(a.od[0], STEM_PT), a.n, ceil_div((cgA + cgB) * 8, STEM_CO));
   if (bf16_storage)
     stem_kernel<__nv_bfloat16><<<grid, 128, smem, st>>>(s);
   else

@@ -537,123 +537,122 @@ tc_conv_kernel(const KArgs a, const __grid_constant__ CUtensorMap tmap0, const _
         if (warp == 0 && chunk < 4) SGM_TRACE(12 + chunk);
         continue;
       }
-      // geometry of an item: validity, output position, brick row
-      auto item_geom = [&](int it, int& t, int& cls, int& piece, int& p, int& o0, int& o1, int& o2) -> bool {
-        piece = it % npiece;
-        const int tc_ = it / npiece;
-        cls = tc_ % a.ncls;
-        t = tc_ / a.ncls;
-        p = a.row_first + (chunk * a.tpc + t) * 128 + warp * 32 + lane;
-        const int h2 = p % a.H[2];
-        const int h01 = p / a.H[2];
-        const int h1 = h01 % a.H[1], h0 = h01 / a.H[1];
-        const int r0 = org[0] + h0 - a.lo[0], r1 = org[1] + h1 - a.lo[1], r2 = org[2] + h2 - a.lo[2];
-        const bool v = h0 >= a.lo[0] && h0 < a.lo[0] + a.t[0] && h1 >= a.lo[1] && h1 < a.lo[1] + a.t[1] &&
-                       h2 >= a.lo[2] && h2 < a.lo[2] + a.t[2] && r0 < a.rd[0] && r1 < a.rd[1] && r2 < a.rd[2];
-        o0 = r0, o1 = r1, o2 = r2;
-        if (a.mode == MODE_T2) {
-          int bits = cls;
-          o2 = 2 * r2 + (bits & 1);
-          bits >>= 1;
-          o1 = 2 * r1 + (bits & 1);
-          bits >>= 1;
-          o0 = a.par[0] == 2 ? 2 * r0 + (bits & 1) : r0;
-        }
-        return v;
-      };
-      uint4 nres[2];  // prefetched global residual (two channel groups) of the next item
-      auto res_prefetch = [&](int it) {
-        int t, cls, piece, p, o0, o1, o2;
-        const bool v = item_geom(it, t, cls, piece, p, o0, o1, o2);
-        const int gcg = (coblk * N + piece * 16) >> 3;
-        nres[0] = nres[1] = make_uint4(0, 0, 0, 0);
-        if (v && gcg < a.segA_cg) {
-          const long long opos = ((long long)o0 * a.od[1] + o1) * a.od[2] + o2;
-          nres[0] = __ldg(reinterpret_cast<const uint4*>(a.res + (((long long)n * a.cgA + gcg) * ovox + opos) * 8));
-          nres[1] = __ldg(reinterpret_cast<const uint4*>(a.res + (((long long)n * a.cgA + gcg + 1) * ovox + opos) * 8));
-        }
-      };
-      if (a.res_mode == 1) res_prefetch(0);
+      // ---- generic path: any N / class count.  Geometry is per tile (hoisted out of the class / piece
+      // loops); the global residual of the next 16-channel piece is prefetched while one is processed.
+      (void)nitems;
       ok = mbar_wait(TFULL(buf), (uint32_t)use & 1u, a.error_flag, 4);
       if (!ok) break;
       tc_fence_after();
       if (warp == 0 && chunk < 4) SGM_TRACE(8 + chunk);  // accumulators of the chunk complete
-      for (int it = 0; it < nitems; ++it) {
-        int t, cls, piece, p, o0, o1, o2;
-        const bool valid = item_geom(it, t, cls, piece, p, o0, o1, o2);
-        const long long opos = ((long long)o0 * a.od[1] + o1) * a.od[2] + o2;
-        const uint32_t tcol = tmem_base + ((uint32_t)(warp * 32) << 16) +
-                              (uint32_t)(buf * a.cols_per_buf + (t * a.ncls + cls) * N + piece * 16);
-        uint32_t raw[16];
-        tc_ld16(tcol, raw);  // warp-collective: every lane executes it
-        const uint4 cres0 = nres[0], cres1 = nres[1];
-        if (a.res_mode == 1 && it + 1 < nitems) res_prefetch(it + 1);
-        const int cbase = coblk * N + piece * 16;  // fused output channel of raw[0]
-        const int gcg = cbase >> 3;
-        const bool segA = gcg < a.segA_cg;
-        float v[16];
+      for (int t = 0; t < tiles_here; ++t) {
+        const int p = a.row_first + (chunk * a.tpc + t) * 128 + warp * 32 + lane;
+        const int h2 = p % a.H[2];
+        const int h01 = p / a.H[2];
+        const int h1 = h01 % a.H[1], h0 = h01 / a.H[1];
+        const int r0 = org[0] + h0 - a.lo[0], r1 = org[1] + h1 - a.lo[1], r2 = org[2] + h2 - a.lo[2];
+        const bool valid = h0 >= a.lo[0] && h0 < a.lo[0] + a.t[0] && h1 >= a.lo[1] && h1 < a.lo[1] + a.t[1] &&
+                           h2 >= a.lo[2] && h2 < a.lo[2] + a.t[2] && r0 < a.rd[0] && r1 < a.rd[1] && r2 < a.rd[2];
+        for (int cls = 0; cls < a.ncls; ++cls) {
+          int o0 = r0, o1 = r1, o2 = r2;
+          if (a.mode == MODE_T2) {
+            int bits = cls;
+            o2 = 2 * r2 + (bits & 1);
+            bits >>= 1;
+            o1 = 2 * r1 + (bits & 1);
+            bits >>= 1;
+            o0 = a.par[0] == 2 ? 2 * r0 + (bits & 1) : r0;
+          }
+          const long long opos = ((long long)o0 * a.od[1] + o1) * a.od[2] + o2;
+          const uint32_t tcol0 = tmem_base + ((uint32_t)(warp * 32) << 16) +
+                                 (uint32_t)(buf * a.cols_per_buf + (t * a.ncls + cls) * N);
+          uint4 nres0 = make_uint4(0, 0, 0, 0), nres1 = nres0;
+          auto res_fetch = [&](int piece) {
+            const int g = (coblk * N + piece * 16) >> 3;
+            if (valid && g < a.segA_cg) {
+              nres0 = __ldg(reinterpret_cast<const uint4*>(a.res + (((long long)n * a.cgA + g) * ovox + opos) * 8));
+              nres1 = __ldg(reinterpret_cast<const uint4*>(a.res + (((long long)n * a.cgA + g + 1) * ovox + opos) * 8));
+            }
+          };
+          if (a.res_mode == 1) res_fetch(0);
+          for (int piece = 0; piece < npiece; ++piece) {
+            uint32_t raw[16];
+            tc_ld16(tcol0 + piece * 16, raw);  // warp-collective: every lane executes it
+            const uint4 cres0 = nres0, cres1 = nres1;
+            if (a.res_mode == 1 && piece + 1 < npiece) res_fetch(piece + 1);
+            if (!valid) continue;
+            const int cbase = coblk * N + piece * 16;  // fused output channel of raw[0]
+            const int gcg = cbase >> 3;
+            const bool segA = gcg < a.segA_cg;
+            float v[16];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          float x = __uint_as_float(raw[c]) + __ldg(a.bias + cbase + c);
-          if (segA && a.actA) x = prelu(x, a.alphaA);
-          v[c] = x;
-        }
-        if (!valid) continue;
-        if (segA) {
-          if (a.res_mode == 1) {
-            float r[8];
-            unpack8(cres0, r);
+            for (int q = 0; q < 4; ++q) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + cbase) + q);
+              v[4 * q + 0] = __uint_as_float(raw[4 * q + 0]) + b4.x;
+              v[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + b4.y;
+              v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + b4.z;
+              v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + b4.w;
+            }
+            if (segA && a.actA) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) v[c] += r[c];
-            unpack8(cres1, r);
+              for (int c = 0; c < 16; ++c) v[c] = prelu(v[c], a.alphaA);
+            }
+            if (segA) {
+              if (a.res_mode == 1) {
+                float r[8];
+                unpack8(cres0, r);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) v[8 + c] += r[c];
-          } else if (a.res_mode == 2) {  // identity residual: centre of the brick, channel group = gcg
+                for (int c = 0; c < 8; ++c) v[c] += r[c];
+                unpack8(cres1, r);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              float r[8];
-              unpack8(*reinterpret_cast<const uint4*>(a_smem + ((size_t)(gcg + h) * a.P + p) * 16), r);
+                for (int c = 0; c < 8; ++c) v[8 + c] += r[c];
+              } else if (a.res_mode == 2) {  // identity residual: centre of the brick, channel group = gcg
 #pragma unroll
-              for (int c = 0; c < 8; ++c) v[h * 8 + c] += r[c];
+                for (int h = 0; h < 2; ++h) {
+                  float r[8];
+                  unpack8(*reinterpret_cast<const uint4*>(a_smem + ((size_t)(gcg + h) * a.P + p) * 16), r);
+#pragma unroll
+                  for (int c = 0; c < 8; ++c) v[h * 8 + c] += r[c];
+                }
+              }
+              if (a.out_kind == OUT_CG8) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                  if (gcg + h < a.cgA)
+                    *reinterpret_cast<uint4*>(a.outA + (((long long)n * a.cgA + gcg + h) * ovox + opos) * 8) =
+                        pack8(v + h * 8);
+              } else if (a.out_kind == OUT_BLEND) {
+                const int g0 = a.wo[0] + o0;
+                if (g0 >= 0 && g0 < a.ad0) {
+                  const long long off = ((long long)g0 * a.ad1 + (a.wo[1] + o1)) * a.ad2 + (a.wo[2] + o2);
+                  const float imw = fmaxf(__fmul_rn(__fmul_rn(a.imap0[o0], a.imap1[o1]), a.imap2[o2]), a.imap_floor);
+                  float oldv[16];
+#pragma unroll
+                  for (int c = 0; c < 16; ++c)
+                    if (cbase + c < a.c_real) oldv[c] = __ldcg(a.pl_out + (cbase + c) * a.pl_cstride + off);
+#pragma unroll
+                  for (int c = 0; c < 16; ++c)  // seg *= w; out += seg (two roundings, as MONAI)
+                    if (cbase + c < a.c_real)
+                      __stcg(a.pl_out + (cbase + c) * a.pl_cstride + off, __fadd_rn(oldv[c], __fmul_rn(v[c], imw)));
+                }
+              } else {  // OUT_PLANAR: fp32 logits [n][C][od], optionally pre-multiplied by the importance map
+                float imw = 1.f;
+                if (a.pl_weighted)
+                  imw = fmaxf(__fmul_rn(__fmul_rn(a.imap0[o0], a.imap1[o1]), a.imap2[o2]), a.imap_floor);
+                const long long off = (long long)n * a.pl_nstride + opos;
+#pragma unroll
+                for (int c = 0; c < 16; ++c)
+                  if (cbase + c < a.c_real)
+                    __stcs(a.pl_out + (cbase + c) * a.pl_cstride + off, a.pl_weighted ? __fmul_rn(v[c], imw) : v[c]);
+              }
+            } else {
+              const int bcg = gcg - a.segA_cg;
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+                if (bcg + h < a.cgB)
+                  *reinterpret_cast<uint4*>(a.outB + (((long long)n * a.cgB + bcg + h) * ovox + opos) * 8) =
+                      pack8(v + h * 8);
             }
           }
-          if (a.out_kind == OUT_CG8) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-              if (gcg + h < a.cgA)
-                *reinterpret_cast<uint4*>(a.outA + (((long long)n * a.cgA + gcg + h) * ovox + opos) * 8) =
-                    pack8(v + h * 8);
-          } else if (a.out_kind == OUT_BLEND) {
-            const int g0 = a.wo[0] + o0;
-            if (g0 >= 0 && g0 < a.ad0) {
-              const long long off = ((long long)g0 * a.ad1 + (a.wo[1] + o1)) * a.ad2 + (a.wo[2] + o2);
-              const float imw = fmaxf(__fmul_rn(__fmul_rn(a.imap0[o0], a.imap1[o1]), a.imap2[o2]), a.imap_floor);
-              float oldv[16];
-#pragma unroll
-              for (int c = 0; c < 16; ++c)
-                if (cbase + c < a.c_real) oldv[c] = __ldcg(a.pl_out + (cbase + c) * a.pl_cstride + off);
-#pragma unroll
-              for (int c = 0; c < 16; ++c)  // seg *= w; out += seg (two roundings, as MONAI)
-                if (cbase + c < a.c_real)
-                  __stcg(a.pl_out + (cbase + c) * a.pl_cstride + off, __fadd_rn(oldv[c], __fmul_rn(v[c], imw)));
-            }
-          } else {  // OUT_PLANAR: fp32 logits [n][C][od], optionally pre-multiplied by the importance map
-            float imw = 1.f;
-            if (a.pl_weighted)
-              imw = fmaxf(__fmul_rn(__fmul_rn(a.imap0[o0], a.imap1[o1]), a.imap2[o2]), a.imap_floor);
-            const long long off = (long long)n * a.pl_nstride + opos;
-#pragma unroll
-            for (int c = 0; c < 16; ++c)
-              if (cbase + c < a.c_real)
-                __stcs(a.pl_out + (cbase + c) * a.pl_cstride + off, a.pl_weighted ? __fmul_rn(v[c], imw) : v[c]);
-          }
-        } else {
-          const int bcg = gcg - a.segA_cg;
-#pragma unroll
-          for (int h = 0; h < 2; ++h)
-            if (bcg + h < a.cgB)
-              *reinterpret_cast<uint4*>(a.outB + (((long long)n * a.cgB + bcg + h) * ovox + opos) * 8) =
-                  pack8(v + h * 8);
         }
       }
       tc_fence_before();
