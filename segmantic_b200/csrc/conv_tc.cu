@@ -22,6 +22,7 @@
 // Accumulators are double-buffered in TMEM so the epilogue of chunk i overlaps the MMAs of chunk i+1;
 // two CTAs per SM overlap brick loads with the other CTA's MMAs.
 #include "conv_tc.cuh"
+#include "tc_ptx.cuh"
 
 #include <cuda.h>  // CUtensorMap (types only; the encoder is resolved through cudaGetDriverEntryPoint)
 
@@ -36,7 +37,7 @@ namespace {
 
 constexpr int kThreads = 192;
 constexpr int kSmemBudget = 110 * 1024;   // two CTAs per SM
-constexpr long long kWaitCycles = 1000000000LL;
+using namespace tcptx;
 
 struct KArgs {
   const __nv_bfloat16* in0;
@@ -80,100 +81,6 @@ struct KArgs {
   long long* trace;   // optional (SGM_TRACE): clock64 stamps of CTA 0's phases
 };
 
-// ------------------------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.b32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must not hang the GPU.  Returns false (and raises the flag) on timeout.
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
-  if (mbar_try_wait(bar, parity)) return true;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > kWaitCycles) {
-      atomicExch(err, code);
-      return false;
-    }
-  }
-  return true;
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                       uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t v[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
-// [0,14) start>>4 | [16,30) LBO>>4 (next 16-byte K chunk) | [32,46) SBO>>4 (next 8-row group) | [46,48) version=1
-__device__ __forceinline__ uint64_t make_desc(uint32_t addr16, uint32_t lbo16, uint32_t sbo16) {
-  const uint32_t lo = (addr16 & 0x3FFFu) | ((lbo16 & 0x3FFFu) << 16);
-  const uint32_t hi = (sbo16 & 0x3FFFu) | (1u << 14);
-  return ((uint64_t)hi << 32) | lo;
-}
-
-__device__ __forceinline__ float prelu(float v, float alpha) { return v > 0.f ? v : alpha * v; }
-
-__device__ __forceinline__ void unpack8(const uint4 v, float x[8]) {
-  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    x[2 * i] = __uint_as_float(w[i] << 16);
-    x[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
-  }
-}
-__device__ __forceinline__ uint4 pack8(const float v[8]) {
-  uint32_t w[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const __nv_bfloat162 b = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-    w[i] = *reinterpret_cast<const uint32_t*>(&b);
-  }
-  return make_uint4(w[0], w[1], w[2], w[3]);
-}
 
 // ------------------------------------------------------------------------------------------ kernel
 // K-block descriptors of every distinct (mode, kernel, channel-pair count) live in constant memory so
@@ -181,43 +88,6 @@ __device__ __forceinline__ uint4 pack8(const float v[8]) {
 constexpr int kBlkConst = 12288;
 __constant__ uint32_t c_blk[kBlkConst];
 
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred P;\n\t"
-      "elect.sync _|P, 0xffffffff;\n\t"
-      "selp.b32 %0, 1, 0, P;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-
-// Bounded wait for the uniform (all-lanes) roles: a timeout aborts the kernel instead of hanging.
-__device__ __forceinline__ void mbar_wait_or_trap(uint32_t bar, uint32_t parity, int* err, int code) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > kWaitCycles) {
-      atomicExch(err, code);
-      __trap();
-    }
-  }
-}
-
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
-                                            uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4,
-                                            uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
 
 __global__ void __launch_bounds__(kThreads, 2)
 tc_conv_kernel(const KArgs a, const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1) {
@@ -693,6 +563,7 @@ static void free_plans(void* p);
 void tc_free(TcConv* c) {
   if (!c) return;
   free_plans(c->plan_cache);
+  nf_free(c);
   if (c->w) cudaFree(c->w);
   if (c->bias) cudaFree(c->bias);
   delete c;
@@ -872,6 +743,13 @@ int tc_pack(const sgm_conv_desc* m, const sgm_conv_desc* second, int spatial_dim
     tc_free(c);
     return SGM_ERR_CUDA;
   }
+  if (!second) {
+    const int rc = nf_pack(*m, c);
+    if (rc) {
+      tc_free(c);
+      return rc;
+    }
+  }
   *out = c;
   return SGM_OK;
 }
@@ -897,7 +775,7 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-static bool tma_available() { return encode_fn() != nullptr; }
+bool tma_available() { return encode_fn() != nullptr; }
 
 struct MapKey {
   const void* ptr;
@@ -909,8 +787,7 @@ struct MapEntry {
 };
 static std::vector<MapEntry> g_maps;
 
-static int make_brick_map(CUtensorMap* out, const void* ptr, int ncg, const int d[3], const int H[3],
-                          const int* par = nullptr) {
+int make_brick_map(CUtensorMap* out, const void* ptr, int ncg, const int d[3], const int H[3], const int* par) {
   MapKey key{ptr, ncg, {d[0], d[1], d[2]}, {H[0], H[1], H[2]}, {par ? par[0] : 0, par ? par[1] : 0, par ? par[2] : 0}};
   for (auto& e : g_maps)
     if (memcmp(&e.key, &key, sizeof(key)) == 0) {
@@ -1074,6 +951,7 @@ static void free_plans(void* p) { delete reinterpret_cast<std::vector<PlanEntry>
 int tc_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t st) {
   SGM_REQUIRE(io.cg0 + io.cg1 == c.cgin, SGM_ERR_INVALID, "tc_launch: input channel groups %d+%d != %d", io.cg0,
               io.cg1, c.cgin);
+  if (nf_applicable(c, io)) return nf_launch(c, io, error_flag_dev, st);
   const int key[8] = {io.id[0], io.id[1], io.id[2], io.od[0], io.od[1], io.od[2], io.n, io.cg0};
   auto* plans = reinterpret_cast<std::vector<PlanEntry>*>(c.plan_cache);
   const PlanEntry* pe = nullptr;

@@ -71,6 +71,20 @@ def main():
         results.append(run_case(net, "s1 256->256 bottom.unit1 6^3", 13, cg8(1, 32, (6, 6, 6), 8, dev)))
         results.append(run_case(net, "k1 128->256 bottom.residual 6^3", 14, cg8(1, 16, (6, 6, 6), 9, dev)))
         results.append(run_case(net, "s1 10->10 head conv 32^3", 22, cg8(1, 2, (32, 32, 32), 10, dev)))
+    if which in ("all", "nf"):
+        # N-fold family (conv_nf.cu): identity residual from the brick centre, global residual, ragged extents
+        x = cg8(1, 2, (48, 48, 48), 30, dev)
+        results.append(run_case(net, "nf 16->16 up1.ru 48^3 identity res", 20, x, res=x))
+        x = cg8(2, 4, (24, 24, 24), 31, dev)
+        results.append(run_case(net, "nf 32->32 up2.ru 24^3 n2 identity res", 18, x, res=x))
+        results.append(run_case(net, "nf 32->32 d1.unit1 24^3 global res", 4, cg8(1, 4, (24, 24, 24), 32, dev),
+                                res=cg8(1, 4, (24, 24, 24), 33, dev)))
+        x = cg8(1, 2, (13, 17, 29), 34, dev)
+        results.append(run_case(net, "nf 16->16 ragged 13x17x29 identity", 20, x, res=x))
+        x = cg8(3, 2, (31, 33, 50), 35, dev)
+        results.append(run_case(net, "nf 10->10 head ragged 31x33x50 n3", 22, x, res=x))
+        x = cg8(2, 2, (96, 96, 96), 36, dev)
+        results.append(run_case(net, "nf 10->10 head 96^3 n2 identity", 22, x, res=x))
     if which in ("all", "s2"):
         results.append(run_case(net, "s2 16->32(+32) d1.unit0 fused 16^3", 3, cg8(1, 2, (16, 16, 16), 11, dev),
                                 fused=True, cg_out2=4))
