@@ -10,7 +10,11 @@ mkdir -p "$HERE/build"
 OBJS=()
 for src in "$HERE"/*.cu; do
   obj="$HERE/build/$(basename "${src%.cu}").o"
-  if [[ ! -f "$obj" || "$src" -nt "$obj" || "$HERE/common.cuh" -nt "$obj" || "$HERE/../../include/segmantic_b200.h" -nt "$obj" ]]; then
+  stale=0
+  for dep in "$src" "$HERE"/*.cuh "$HERE/../../include/segmantic_b200.h"; do
+    if [[ ! -f "$obj" || "$dep" -nt "$obj" ]]; then stale=1; fi
+  done
+  if [[ $stale == 1 ]]; then
     "$NVCC" "${FLAGS[@]}" ${SGM_PTXAS_V:+-Xptxas -v} -c "$src" -o "$obj" &
   fi
   OBJS+=("$obj")

@@ -41,12 +41,12 @@ struct TcConv {
   int c_real = 0;             // real (unpadded) channels of segment A
   int blk_off = -1;           // slice of the constant K-block bank
   void* plan_cache = nullptr; // launch geometry per (dims, batch), filled lazily by tc_launch
-  // "N-fold" packing (conv_nf.cu): stride-1 3x3x3 convs with <= 32 output channels fold the three d2 taps
-  // into the MMA N dimension (9 instead of 27 MMAs per K block, one third of the shared-memory A traffic)
-  __nv_bfloat16* nf_w = nullptr;  // device [9*ncgp][2][NP][8], row n' = k2*CS + co
-  int nf_cs = 0;                  // column stride per d2 tap (8, 16, 24 or 32); 0 = not eligible
-  int nf_ncgp = 0;                // input channel pairs of groups (cin padded to 16*ncgp)
-  void* nf_plan_cache = nullptr;
+  // "plane-sweep" packing (conv_ps.cu): stride-1 3x3x3 convs with <= 32 channels fold the three d0 taps
+  // into the MMA N dimension (9 instead of 27 MMAs per 16 input channels) and sweep the window along d0
+  __nv_bfloat16* ps_w = nullptr;  // device [9*ncgp][2][NP][8], row n' = k0*CB + co
+  int ps_cb = 0;                  // columns per d0 tap (4, 8, 10, 16, 20, 24 or 32); 0 = not eligible
+  int ps_ncgp = 0;                // input channel pairs of groups (cin padded to 16*ncgp)
+  void* ps_plan_cache = nullptr;
 };
 
 struct TcIO {
@@ -83,11 +83,11 @@ bool tma_available();
 int make_brick_map(CUtensorMap* out, const void* ptr, int ncg, const int d[3], const int H[3],
                    const int* par = nullptr);
 
-// N-fold family (conv_nf.cu)
-int nf_pack(const sgm_conv_desc& d, TcConv* c);          // fills nf_* when the conv is eligible (else leaves nf_cs = 0)
-bool nf_applicable(const TcConv& c, const TcIO& io);
-int nf_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t st);
-void nf_free(TcConv* c);
+// plane-sweep family (conv_ps.cu)
+int ps_pack(const sgm_conv_desc& d, TcConv* c);          // fills ps_* when the conv is eligible (else leaves ps_cb = 0)
+bool ps_applicable(const TcConv& c, const TcIO& io);
+int ps_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t st);
+void ps_free(TcConv* c);
 
 }  // namespace tc
 }  // namespace sgm

@@ -71,20 +71,35 @@ def main():
         results.append(run_case(net, "s1 256->256 bottom.unit1 6^3", 13, cg8(1, 32, (6, 6, 6), 8, dev)))
         results.append(run_case(net, "k1 128->256 bottom.residual 6^3", 14, cg8(1, 16, (6, 6, 6), 9, dev)))
         results.append(run_case(net, "s1 10->10 head conv 32^3", 22, cg8(1, 2, (32, 32, 32), 10, dev)))
-    if which in ("all", "nf"):
-        # N-fold family (conv_nf.cu): identity residual from the brick centre, global residual, ragged extents
+    if which in ("all", "ps"):
+        # plane-sweep family (conv_ps.cu): identity residual from the brick centre, global residual, ragged extents
         x = cg8(1, 2, (48, 48, 48), 30, dev)
-        results.append(run_case(net, "nf 16->16 up1.ru 48^3 identity res", 20, x, res=x))
+        results.append(run_case(net, "ps 16->16 up1.ru 48^3 identity res", 20, x, res=x))
         x = cg8(2, 4, (24, 24, 24), 31, dev)
-        results.append(run_case(net, "nf 32->32 up2.ru 24^3 n2 identity res", 18, x, res=x))
-        results.append(run_case(net, "nf 32->32 d1.unit1 24^3 global res", 4, cg8(1, 4, (24, 24, 24), 32, dev),
+        results.append(run_case(net, "ps 32->32 up2.ru 24^3 n2 identity res", 18, x, res=x))
+        results.append(run_case(net, "ps 32->32 d1.unit1 24^3 global res", 4, cg8(1, 4, (24, 24, 24), 32, dev),
                                 res=cg8(1, 4, (24, 24, 24), 33, dev)))
         x = cg8(1, 2, (13, 17, 29), 34, dev)
-        results.append(run_case(net, "nf 16->16 ragged 13x17x29 identity", 20, x, res=x))
+        results.append(run_case(net, "ps 16->16 ragged 13x17x29 identity", 20, x, res=x))
         x = cg8(3, 2, (31, 33, 50), 35, dev)
-        results.append(run_case(net, "nf 10->10 head ragged 31x33x50 n3", 22, x, res=x))
+        results.append(run_case(net, "ps 10->10 head ragged 31x33x50 n3", 22, x, res=x))
         x = cg8(2, 2, (96, 96, 96), 36, dev)
-        results.append(run_case(net, "nf 10->10 head 96^3 n2 identity", 22, x, res=x))
+        results.append(run_case(net, "ps 10->10 head 96^3 n2 identity", 22, x, res=x))
+        # small extents (the 32^3-roi tests): few planes per column, few units
+        results.append(run_case(net, "ps 16->16 d0.unit1 16^3 n2 global res", 1, cg8(2, 2, (16, 16, 16), 37, dev),
+                                res=cg8(2, 2, (16, 16, 16), 38, dev)))
+        x = cg8(2, 2, (16, 16, 16), 39, dev)
+        results.append(run_case(net, "ps 16->16 up1.ru 16^3 n2 identity", 20, x, res=x))
+        results.append(run_case(net, "ps 32->32 d1.unit1 8^3 n2 global res", 4, cg8(2, 4, (8, 8, 8), 40, dev),
+                                res=cg8(2, 4, (8, 8, 8), 41, dev)))
+        x = cg8(2, 4, (8, 8, 8), 42, dev)
+        results.append(run_case(net, "ps 32->32 up2.ru 8^3 n2 identity", 18, x, res=x))
+        x = cg8(2, 2, (32, 32, 32), 43, dev)
+        results.append(run_case(net, "ps 10->10 head 32^3 n2 identity", 22, x, res=x))
+        x = cg8(1, 2, (5, 7, 3), 44, dev)
+        results.append(run_case(net, "ps 16->16 tiny 5x7x3 identity", 20, x, res=x))
+        x = cg8(1, 2, (1, 9, 9), 45, dev)
+        results.append(run_case(net, "ps 16->16 one plane 1x9x9 identity", 20, x, res=x))
     if which in ("all", "s2"):
         results.append(run_case(net, "s2 16->32(+32) d1.unit0 fused 16^3", 3, cg8(1, 2, (16, 16, 16), 11, dev),
                                 fused=True, cg_out2=4))
