@@ -59,7 +59,11 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.
+
+    The nvidia-smi process is started well before the timed region (its NVML start-up can take hundreds of
+    milliseconds and perturbs concurrent launches); only the rows that arrive between begin() and end()
+    are reported."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -67,28 +71,39 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            deadline = time.time() + 10.0
+            while not self.rows and time.time() < deadline:  # wait for the first sample: start-up is over
+                time.sleep(0.02)
         except Exception as e:  # noqa: BLE001
             log("clock sampler unavailable:", e)
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
+
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if not self.proc:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["unavailable"])
-        time.sleep(0.12)
+        time.sleep(0.05)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        rows = [r for (t, r) in self.rows if self.t0 is None or (self.t0 <= t <= (self.t1 or t) + 0.03)]
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -256,22 +271,24 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(3, args.warmup)):
         step()
     net.check()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     net.set_profiling(not args.no_profile)
     net.get_profile()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.begin()
     ev0.record()
     for _ in range(args.steps):
         out = step()
     ev1.record()
     barrier()
+    sampler.end()
     ms = ev0.elapsed_time(ev1) / args.steps
     launches_step = net.last_launch_count  # network launches + the gather-blend kernel
     prof = net.get_profile()
@@ -366,7 +383,7 @@ def run_b200(args):
         blend_bytes = 4.0 * CLASSES * n_win * roi_vox + float(np.prod(VOL))
         if blend_prof[2] > 0 and blend_prof[1] > 0:
             t = blend_prof[1] * 1e-3 / blend_prof[2]
-            blend_roof = dict(kernel="gather_blend_kernel[sum covering windows + count + normalise + argmax]",
+            blend_roof = dict(kernel="gather_blend_cw_kernel[sum covering windows + count + normalise + argmax]",
                               bound="hbm", achieved=blend_bytes / t / 1e9, peak=pk["hbm"], unit="GB/s",
                               frac=blend_bytes / t / 1e9 / pk["hbm"], traffic=None, peak_source=pk["source"],
                               ms_per_launch=t * 1e3, algorithmic_bytes_per_launch=blend_bytes,
@@ -404,7 +421,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])

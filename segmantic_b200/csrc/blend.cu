@@ -122,175 +122,157 @@ struct GatherArgs {
   float floor;
 };
 
-__device__ __forceinline__ int covering2(const int* starts, int ns, int roi, int v, int* loc, int* idx) {
-  int c = 0;
+// One warp per channel: lane l owns VEC consecutive voxels of a z-chunk, warp w sums channel w (w + W, ...) of
+// those voxels over the covering windows -- every (window, channel) read of a warp is one contiguous 128 / 512
+// byte run, a thread keeps only VEC accumulators and its window loads are independent.  The windows that cover
+// a coordinate are a contiguous range of the (sorted) per-axis starts, so the covering sets are two integers per
+// axis: no per-thread index arrays (the first version kept them in local memory and executed 1200 instructions
+// per warp and chunk).  A block owns one (x, y) row: the axis-0 / axis-1 ranges and the count map of the row are
+// computed once and shared; the normalised values meet in shared memory for the argmax / softmax across channels.
+// VEC = 4 needs dims[2], roi[2] and every axis-2 window start to be multiples of 4 (aligned float4).
+constexpr int kGatherWarps = 16;
+
+// windows j in [lo, hi] cover v  (starts ascending: start[j] <= v < start[j] + roi)
+__device__ __forceinline__ void cover_range(const int* starts, int ns, int roi, int v, int& lo, int& hi) {
+  lo = ns, hi = -1;
   for (int j = 0; j < ns; ++j) {
     const int s = starts[j];
-    if (s <= v && v < s + roi && c < MAX_COVER) {
-      loc[c] = v - s;
-      idx[c] = j;
-      ++c;
-    }
-  }
-  return c;
-}
-
-template <int CMAX>
-__global__ void __launch_bounds__(256) gather_blend_kernel(const GatherArgs a) {
-  const long long vox = (long long)a.nx * a.d1 * a.d2;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < vox; v += stride) {
-    const int z = (int)(v % a.d2);
-    const long long t = v / a.d2;
-    const int y = (int)(t % a.d1);
-    const int x = (int)(t / a.d1) + a.x0;
-    int l0[MAX_COVER], l1[MAX_COVER], l2[MAX_COVER], j0[MAX_COVER], j1[MAX_COVER], j2[MAX_COVER];
-    const int c0 = covering2(a.starts, a.n_starts[0], a.roi[0], x, l0, j0);
-    const int c1 = covering2(a.starts + SGM_MAX_STARTS, a.n_starts[1], a.roi[1], y, l1, j1);
-    const int c2 = covering2(a.starts + 2 * SGM_MAX_STARTS, a.n_starts[2], a.roi[2], z, l2, j2);
-    float acc[CMAX];
-#pragma unroll
-    for (int c = 0; c < CMAX; ++c) acc[c] = 0.f;
-    float count = 0.f;
-    for (int p = 0; p < c0; ++p) {
-      const float g0 = a.imap0[l0[p]];
-      const bool have = j0[p] >= a.a0_begin && j0[p] < a.a0_end;
-      for (int q = 0; q < c1; ++q) {
-        const float g01 = __fmul_rn(g0, a.imap1[l1[q]]);
-        for (int r = 0; r < c2; ++r) {
-          count = __fadd_rn(count, fmaxf(__fmul_rn(g01, a.imap2[l2[r]]), a.floor));
-          if (!have) continue;
-          const long long w = ((long long)(j0[p] - a.a0_begin) * a.n_starts[1] + j1[q]) * a.n_starts[2] + j2[r];
-          const float* src = a.wl + w * a.win_stride + ((long long)l0[p] * a.roi[1] + l1[q]) * a.roi[2] + l2[r];
-#pragma unroll
-          for (int c = 0; c < CMAX; ++c)
-            if (c < a.channels) acc[c] = __fadd_rn(acc[c], __ldcs(src + c * a.cstride));
-        }
-      }
-    }
-    float best = 0.f;
-    int arg = 0;
-#pragma unroll
-    for (int c = 0; c < CMAX; ++c) {
-      if (c < a.channels) {
-        acc[c] = __fdiv_rn(acc[c], count);
-        if (c == 0 || acc[c] > best) best = acc[c], arg = c;
-      }
-    }
-    if (a.labels) a.labels[v] = (uint8_t)arg;
-    if (a.logits) {
-#pragma unroll
-      for (int c = 0; c < CMAX; ++c)
-        if (c < a.channels) __stcs(a.logits + c * vox + v, acc[c]);
-    }
-    if (a.probs) {
-      float sum = 0.f;
-#pragma unroll
-      for (int c = 0; c < CMAX; ++c)
-        if (c < a.channels) {
-          acc[c] = expf(acc[c] - best);
-          sum += acc[c];
-        }
-      const float inv = 1.f / sum;
-#pragma unroll
-      for (int c = 0; c < CMAX; ++c)
-        if (c < a.channels) __stcs(a.probs + c * vox + v, acc[c] * inv);
+    if (s <= v && v < s + roi) {
+      lo = min(lo, j);
+      hi = j;
     }
   }
 }
 
-// Vectorised form: one thread owns 4 consecutive voxels along the fastest axis and moves 16 bytes per
-// (window, channel) -- the scalar form is bound by load-instruction issue (one 4-byte LDG per lane per
-// window-channel), not by HBM.  Needs roi[2], dims[2] and every axis-2 window start to be multiples of 4
-// (then the 4 voxels share their covering windows and every float4 is aligned).
-template <int CMAX>
-__global__ void __launch_bounds__(256) gather_blend_kernel_v4(const GatherArgs a) {
-  const int d2q = a.d2 >> 2;
+template <int VEC>
+__global__ void __launch_bounds__(kGatherWarps * 32) gather_blend_cw_kernel(const GatherArgs a, int nwarps) {
+  extern __shared__ float dyn[];  // [2][channels][32 * VEC] values | [d2] count map of the row
+  __shared__ int s_st[3][SGM_MAX_STARTS];
+  __shared__ float s_im[3][512];
+  constexpr int CH = 32 * VEC;  // voxels per z-chunk
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int C = a.channels;
+  float* vals = dyn;
+  float* s_count = dyn + (size_t)2 * C * CH;
+  for (int i = threadIdx.x; i < 3 * SGM_MAX_STARTS; i += blockDim.x) s_st[i / SGM_MAX_STARTS][i % SGM_MAX_STARTS] = a.starts[i];
+  for (int i = threadIdx.x; i < a.roi[0]; i += blockDim.x) s_im[0][i] = a.imap0[i];
+  for (int i = threadIdx.x; i < a.roi[1]; i += blockDim.x) s_im[1][i] = a.imap1[i];
+  for (int i = threadIdx.x; i < a.roi[2]; i += blockDim.x) s_im[2][i] = a.imap2[i];
+  __syncthreads();
   const long long vox = (long long)a.nx * a.d1 * a.d2;
-  const long long nq = (long long)a.nx * a.d1 * d2q;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long qi = (long long)blockIdx.x * blockDim.x + threadIdx.x; qi < nq; qi += stride) {
-    const int zq = (int)(qi % d2q);
-    const long long t = qi / d2q;
-    const int y = (int)(t % a.d1);
-    const int xl = (int)(t / a.d1);
-    const int x = xl + a.x0, z = zq * 4;
-    int l0[MAX_COVER], l1[MAX_COVER], l2[MAX_COVER], j0[MAX_COVER], j1[MAX_COVER], j2[MAX_COVER];
-    const int c0 = covering2(a.starts, a.n_starts[0], a.roi[0], x, l0, j0);
-    const int c1 = covering2(a.starts + SGM_MAX_STARTS, a.n_starts[1], a.roi[1], y, l1, j1);
-    const int c2 = covering2(a.starts + 2 * SGM_MAX_STARTS, a.n_starts[2], a.roi[2], z, l2, j2);
-    float acc[CMAX][4];
+  const int nchunks = (a.d2 + CH - 1) / CH;
+  const long long nrows = (long long)a.nx * a.d1;
+  int buf = 0;
+  for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const int y = (int)(row % a.d1);
+    const int xl = (int)(row / a.d1);
+    const int x = xl + a.x0;
+    int p_lo, p_hi, q_lo, q_hi;
+    cover_range(s_st[0], a.n_starts[0], a.roi[0], x, p_lo, p_hi);
+    cover_range(s_st[1], a.n_starts[1], a.roi[1], y, q_lo, q_hi);
+    // ---- count map of the row, MONAI's window order and roundings (all threads, VEC voxels each)
+    for (int z = threadIdx.x * VEC; z < a.d2; z += blockDim.x * VEC) {
+      int r_lo, r_hi;
+      cover_range(s_st[2], a.n_starts[2], a.roi[2], z, r_lo, r_hi);
+      float count[VEC];
 #pragma unroll
-    for (int c = 0; c < CMAX; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f;
-    float count[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int p = 0; p < c0; ++p) {
-      const float g0 = a.imap0[l0[p]];
-      const bool have = j0[p] >= a.a0_begin && j0[p] < a.a0_end;
-      for (int q = 0; q < c1; ++q) {
-        const float g01 = __fmul_rn(g0, a.imap1[l1[q]]);
-        for (int r = 0; r < c2; ++r) {
-          const float4 g2 = *reinterpret_cast<const float4*>(a.imap2 + l2[r]);
-          count[0] = __fadd_rn(count[0], fmaxf(__fmul_rn(g01, g2.x), a.floor));
-          count[1] = __fadd_rn(count[1], fmaxf(__fmul_rn(g01, g2.y), a.floor));
-          count[2] = __fadd_rn(count[2], fmaxf(__fmul_rn(g01, g2.z), a.floor));
-          count[3] = __fadd_rn(count[3], fmaxf(__fmul_rn(g01, g2.w), a.floor));
-          if (!have) continue;
-          const long long w = ((long long)(j0[p] - a.a0_begin) * a.n_starts[1] + j1[q]) * a.n_starts[2] + j2[r];
-          const float* src = a.wl + w * a.win_stride + ((long long)l0[p] * a.roi[1] + l1[q]) * a.roi[2] + l2[r];
-          float4 x4[CMAX];
+      for (int i = 0; i < VEC; ++i) count[i] = 0.f;
+      for (int p = p_lo; p <= p_hi; ++p) {
+        const float g0 = s_im[0][x - s_st[0][p]];
+        for (int q = q_lo; q <= q_hi; ++q) {
+          const float g01 = __fmul_rn(g0, s_im[1][y - s_st[1][q]]);
+          for (int r = r_lo; r <= r_hi; ++r) {
+            const int l2 = z - s_st[2][r];
 #pragma unroll
-          for (int c = 0; c < CMAX; ++c)
-            if (c < a.channels) x4[c] = __ldcs(reinterpret_cast<const float4*>(src + c * a.cstride));
-#pragma unroll
-          for (int c = 0; c < CMAX; ++c)
-            if (c < a.channels) {
-              acc[c][0] = __fadd_rn(acc[c][0], x4[c].x);
-              acc[c][1] = __fadd_rn(acc[c][1], x4[c].y);
-              acc[c][2] = __fadd_rn(acc[c][2], x4[c].z);
-              acc[c][3] = __fadd_rn(acc[c][3], x4[c].w);
-            }
-        }
-      }
-    }
-    const long long v = ((long long)xl * a.d1 + y) * a.d2 + z;
-    float best[4];
-    int arg[4] = {0, 0, 0, 0};
-#pragma unroll
-    for (int c = 0; c < CMAX; ++c) {
-      if (c < a.channels) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          acc[c][i] = __fdiv_rn(acc[c][i], count[i]);
-          if (c == 0 || acc[c][i] > best[i]) best[i] = acc[c][i], arg[i] = c;
-        }
-      }
-    }
-    if (a.labels)
-      *reinterpret_cast<uchar4*>(a.labels + v) = make_uchar4((uint8_t)arg[0], (uint8_t)arg[1], (uint8_t)arg[2], (uint8_t)arg[3]);
-    if (a.logits) {
-#pragma unroll
-      for (int c = 0; c < CMAX; ++c)
-        if (c < a.channels)
-          __stcs(reinterpret_cast<float4*>(a.logits + c * vox + v), make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]));
-    }
-    if (a.probs) {
-      float sum[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int c = 0; c < CMAX; ++c)
-        if (c < a.channels) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            acc[c][i] = expf(acc[c][i] - best[i]);
-            sum[i] += acc[c][i];
+            for (int i = 0; i < VEC; ++i) count[i] = __fadd_rn(count[i], fmaxf(__fmul_rn(g01, s_im[2][l2 + i]), a.floor));
           }
         }
+      }
 #pragma unroll
-      for (int c = 0; c < CMAX; ++c)
-        if (c < a.channels)
-          __stcs(reinterpret_cast<float4*>(a.probs + c * vox + v),
-                 make_float4(acc[c][0] * (1.f / sum[0]), acc[c][1] * (1.f / sum[1]), acc[c][2] * (1.f / sum[2]),
-                             acc[c][3] * (1.f / sum[3])));
+      for (int i = 0; i < VEC; ++i) s_count[z + i] = count[i];
     }
+    __syncthreads();
+    // windows of this rank only (multi-GPU slabs blend a sub-range of the axis-0 starts)
+    const int pa = max(p_lo, a.a0_begin), pb = min(p_hi, a.a0_end - 1);
+    for (int ch = 0; ch < nchunks; ++ch, buf ^= 1) {
+      const int z = ch * CH + lane * VEC;
+      const bool zin = z < a.d2;
+      int r_lo = 0, r_hi = -1;
+      if (zin) cover_range(s_st[2], a.n_starts[2], a.roi[2], z, r_lo, r_hi);
+      float* vb = vals + (size_t)buf * C * CH;
+      for (int c = warp; c < C; c += nwarps) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        const float* wl_c = a.wl + (long long)c * a.cstride;
+        for (int p = pa; p <= pb; ++p) {
+          const long long w0 = (long long)(p - a.a0_begin) * a.n_starts[1];
+          const long long off0 = (long long)(x - s_st[0][p]) * a.roi[1];
+          for (int q = q_lo; q <= q_hi; ++q) {
+            const float* src01 = wl_c + (w0 + q) * a.n_starts[2] * a.win_stride + (off0 + (y - s_st[1][q])) * a.roi[2] + z;
+            // up to three axis-2 windows (overlap <= 0.5) are loaded before the first add; the adds keep MONAI's order
+            float4 v[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+              const int r = r_lo + k;
+              if (r <= r_hi) {
+                const float* src = src01 + r * a.win_stride - s_st[2][r];
+                if (VEC == 4) v[k] = __ldcs(reinterpret_cast<const float4*>(src));
+                else v[k].x = __ldcs(src);
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+              if (r_lo + k <= r_hi) {
+                acc[0] = __fadd_rn(acc[0], v[k].x);
+                if (VEC == 4) acc[1] = __fadd_rn(acc[1], v[k].y), acc[2] = __fadd_rn(acc[2], v[k].z), acc[3] = __fadd_rn(acc[3], v[k].w);
+              }
+            for (int r = r_lo + 3; r <= r_hi; ++r) {
+              const float* src = src01 + r * a.win_stride - s_st[2][r];
+              if (VEC == 4) {
+                const float4 t = __ldcs(reinterpret_cast<const float4*>(src));
+                acc[0] = __fadd_rn(acc[0], t.x), acc[1] = __fadd_rn(acc[1], t.y);
+                acc[2] = __fadd_rn(acc[2], t.z), acc[3] = __fadd_rn(acc[3], t.w);
+              } else {
+                acc[0] = __fadd_rn(acc[0], __ldcs(src));
+              }
+            }
+          }
+        }
+        if (zin) {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) acc[i] = __fdiv_rn(acc[i], s_count[z + i]);
+          const long long v = ((long long)xl * a.d1 + y) * a.d2 + z;
+          if (VEC == 4) {
+            *reinterpret_cast<float4*>(vb + c * CH + lane * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            if (a.logits) __stcs(reinterpret_cast<float4*>(a.logits + c * vox + v), make_float4(acc[0], acc[1], acc[2], acc[3]));
+          } else {
+            vb[c * CH + lane] = acc[0];
+            if (a.logits) __stcs(a.logits + c * vox + v, acc[0]);
+          }
+        }
+      }
+      __syncthreads();  // double-buffered: the next chunk writes the other half while this one is reduced
+      // ---- argmax (ties -> lowest class, as torch.argmax) / softmax across channels: one voxel per thread
+      for (int t = threadIdx.x; t < CH; t += blockDim.x) {
+        const int zz = ch * CH + t;
+        if (zz >= a.d2) continue;
+        float best = vb[t];
+        int arg = 0;
+        for (int c = 1; c < C; ++c) {
+          const float f = vb[c * CH + t];
+          if (f > best) best = f, arg = c;
+        }
+        const long long v = ((long long)xl * a.d1 + y) * a.d2 + zz;
+        if (a.labels) a.labels[v] = (uint8_t)arg;
+        if (a.probs) {
+          float sum = 0.f;
+          for (int c = 0; c < C; ++c) sum += expf(vb[c * CH + t] - best);
+          const float inv = 1.f / sum;
+          for (int c = 0; c < C; ++c) __stcs(a.probs + c * vox + v, expf(vb[c * CH + t] - best) * inv);
+        }
+      }
+    }
+    __syncthreads();  // the count map of the row is rewritten next
   }
 }
 
@@ -309,35 +291,27 @@ int launch_gather_blend(const float* wl, int channels, const sgm_sw_cfg* cfg, co
   a.starts = starts_dev;
   a.imap0 = imap_dev[0], a.imap1 = imap_dev[1], a.imap2 = imap_dev[2];
   a.floor = cfg->imap_floor;
-  const long long vox = (long long)a.nx * a.d1 * a.d2;
-  bool vec4 = (a.d2 % 4 == 0) && (a.roi[2] % 4 == 0) && channels <= 16;
+  bool vec4 = (a.d2 % 4 == 0) && (a.roi[2] % 4 == 0);
   for (int j = 0; j < cfg->n_starts[2]; ++j) vec4 = vec4 && (cfg->starts[2][j] % 4 == 0);
-  if (vec4) {
-    const int blocks4 = (int)std::max<long long>(1, std::min<long long>((vox / 4 + 255) / 256, 148LL * 8 * 8));
-    if (channels <= 4)
-      gather_blend_kernel_v4<4><<<blocks4, 256, 0, st>>>(a);
-    else if (channels <= 8)
-      gather_blend_kernel_v4<8><<<blocks4, 256, 0, st>>>(a);
-    else
-      gather_blend_kernel_v4<16><<<blocks4, 256, 0, st>>>(a);
-    SGM_CUDA_CHECK(cudaGetLastError());
-    return SGM_OK;
-  }
-  int blocks = (int)std::min<long long>((vox + 255) / 256, 148LL * 8 * 8);
-  if (blocks < 1) blocks = 1;
-  if (channels <= 4)
-    gather_blend_kernel<4><<<blocks, 256, 0, st>>>(a);
-  else if (channels <= 8)
-    gather_blend_kernel<8><<<blocks, 256, 0, st>>>(a);
-  else if (channels <= 16)
-    gather_blend_kernel<16><<<blocks, 256, 0, st>>>(a);
-  else if (channels <= 32)
-    gather_blend_kernel<32><<<blocks, 256, 0, st>>>(a);
-  else if (channels <= 64)
-    gather_blend_kernel<64><<<blocks, 256, 0, st>>>(a);
-  else {
+  if (channels > 64) {
     set_error("deferred blend supports at most 64 classes, got %d", channels);
     return SGM_ERR_UNSUPPORTED;
+  }
+  const int nwarps = std::min(channels, kGatherWarps);
+  const long long nrows = (long long)a.nx * a.d1;
+  const int blocks = (int)std::max<long long>(1, std::min<long long>(nrows, 148LL * 64));
+  const size_t smem = ((size_t)2 * channels * 32 * (vec4 ? 4 : 1) + (size_t)a.d2 + 8) * sizeof(float);
+  SGM_REQUIRE(smem <= 96 * 1024, SGM_ERR_UNSUPPORTED, "deferred blend: axis 2 of %d voxels does not fit shared memory", a.d2);
+  static bool attr = false;
+  if (!attr) {
+    SGM_CUDA_CHECK(cudaFuncSetAttribute(gather_blend_cw_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    SGM_CUDA_CHECK(cudaFuncSetAttribute(gather_blend_cw_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr = true;
+  }
+  if (vec4) {
+    gather_blend_cw_kernel<4><<<blocks, nwarps * 32, smem, st>>>(a, nwarps);
+  } else {
+    gather_blend_cw_kernel<1><<<blocks, nwarps * 32, smem, st>>>(a, nwarps);
   }
   SGM_CUDA_CHECK(cudaGetLastError());
   return SGM_OK;

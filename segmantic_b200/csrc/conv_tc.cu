@@ -110,6 +110,7 @@ tc_conv_kernel(const KArgs a, const __grid_constant__ CUtensorMap tmap0, const _
   uint64_t* bars = reinterpret_cast<uint64_t*>(w_smem + a.nstages * a.w_stage_bytes);
   // bars: [0,nstages) wfull, [nstages,2nstages) wempty, then tfull[2], tempty[2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * a.nstages + 5);
+  uint2* blk_tab = reinterpret_cast<uint2*>(bars + 2 * a.nstages + 6);  // per K block: {A offset, accumulator column | overwrite}
   const uint32_t bar0 = smem_u32(bars);
   auto WFULL = [&](int s) { return bar0 + 8u * s; };
   auto WEMPTY = [&](int s) { return bar0 + 8u * (a.nstages + s); };
@@ -183,6 +184,15 @@ tc_conv_kernel(const KArgs a, const __grid_constant__ CUtensorMap tmap0, const _
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
   }
+  // K-block table: everything the issuer needs per MMA that does not depend on the tile, decoded once
+  // (decoding the descriptor words inside the issue loop cost ~200 clk per MMA: the loop was issue-bound)
+  for (int b = tid; b < a.nblk; b += kThreads) {
+    const uint32_t d = c_blk[a.blk_off + b];
+    const int s0 = (int)(d & 3u) - 1, s1 = (int)((d >> 2) & 3u) - 1, s2 = (int)((d >> 4) & 3u) - 1;
+    const int slab = (d >> 6) & 7u, cls = (d >> 9) & 7u, cgpair = (d >> 16) & 0xffu;
+    const int a16 = (slab * a.cgin + cgpair * 2) * a.P + a.row_first + s0 * a.H[1] * a.H[2] + s1 * a.H[2] + s2;
+    blk_tab[b] = make_uint2((uint32_t)a16, (uint32_t)(cls * a.N) | (((d >> 12) & 1u) << 31));
+  }
   // zero the tail the last M tile may read (keeps garbage rows finite; they are discarded anyway)
   for (int it = a.nslab * a.cgin * a.P + tid; it < a.a_units; it += kThreads)
     *reinterpret_cast<uint4*>(a_smem + (size_t)it * 16) = make_uint4(0, 0, 0, 0);
@@ -249,7 +259,6 @@ tc_conv_kernel(const KArgs a, const __grid_constant__ CUtensorMap tmap0, const _
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t a_base16 = smem_u32(a_smem) >> 4;
       const uint32_t w_base16 = smem_u32(w_smem) >> 4;
-      const int H12 = a.H[1] * a.H[2];
       const uint32_t desc_hi = 8u | (1u << 14);                 // SBO = 128 B, version 1
       const uint32_t a_lbo = ((uint32_t)a.P & 0x3FFFu) << 16;   // next channel group of the brick
       const uint32_t b_lbo = ((uint32_t)N & 0x3FFFu) << 16;     // next 8 input channels of the filter block
@@ -273,15 +282,15 @@ tc_conv_kernel(const KArgs a, const __grid_constant__ CUtensorMap tmap0, const _
           }
           const int bend = min(a.nblk, (g + 1) * a.G);
           uint32_t b_lo = (w_base16 + (uint32_t)(stage * a.w_stage_bytes) / 16u) | b_lbo;
+          const uint32_t a_chunk = (a_base16 + (uint32_t)(chunk * a.tpc * 128)) | a_lbo;  // < 2^14 units: no masking
+          const uint32_t col_chunk = tmem_base + (uint32_t)(buf * a.cols_per_buf);
+#pragma unroll 2
           for (int b = g * a.G; b < bend; ++b, b_lo += (uint32_t)(N * 2)) {
-            const uint32_t d = c_blk[a.blk_off + b];
-            const int s0 = (int)(d & 3u) - 1, s1 = (int)((d >> 2) & 3u) - 1, s2 = (int)((d >> 4) & 3u) - 1;
-            const int slab = (d >> 6) & 7u, cls = (d >> 9) & 7u, cgpair = (d >> 16) & 0xffu;
-            const uint32_t acc = ((d >> 12) & 1u) ? 0u : 1u;
-            const int a16 = (slab * a.cgin + cgpair * 2) * a.P + a.row_first + s0 * H12 + s1 * a.H[2] + s2;
+            const uint2 e = blk_tab[b];
+            const uint32_t acc = (e.y >> 31) ? 0u : 1u;
             const uint64_t bdesc = ((uint64_t)desc_hi << 32) | b_lo;
-            uint32_t a_lo = (a_base16 + (uint32_t)(a16 + chunk * a.tpc * 128)) | a_lbo;
-            uint32_t col = tmem_base + (uint32_t)(buf * a.cols_per_buf + cls * N);
+            uint32_t a_lo = a_chunk + e.x;
+            uint32_t col = col_chunk + (e.y & 0xffffu);
 #pragma unroll 4
             for (int t = 0; t < tiles_here; ++t, a_lo += 128u, col += tile_cols)
               tc_mma(col, ((uint64_t)desc_hi << 32) | a_lo, bdesc, idesc, acc);
@@ -889,7 +898,7 @@ static int tc_plan(const TcConv& c, const TcIO& io, KArgs& a, int& smem_bytes_ou
   static const int cand[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64, 96};
   double best = 1e30;
   int bt[3] = {0, 0, 0};
-  const int fixed_bytes = a.nstages * a.w_stage_bytes + (2 * a.nstages + 5) * 8 + 16 + 256;
+  const int fixed_bytes = a.nstages * a.w_stage_bytes + (2 * a.nstages + 6) * 8 + nblk * 8 + 16 + 256;
   a.use_tma = tma_available() && !(c.mode == MODE_S2 && getenv("SGM_NO_TMA_S2"));
   for (int c0 : cand)
     for (int c1 : cand)
