@@ -51,6 +51,7 @@ struct KArgs {
   int P, nslab;
   int row_first, ntiles, tpc, nchunks, nbuf, ncls, cols_per_buf, tmem_cols;
   int N, nblk, G, ngroups, nstages, resident;
+  int mmaN;           // MMA N: N, or ncls * N when the output parity classes of a transposed conv are folded into one MMA
   int blk_off;        // offset of this conv's K-block descriptors in c_blk
   const __nv_bfloat16* w;
   const float* bias;
@@ -235,7 +236,8 @@ tc_conv_kernel(const KArgs a, const __grid_constant__ CUtensorMap tmap0, const _
           }
         }
       }
-      const __nv_bfloat16* wsrc = a.w + (size_t)coblk * a.nblk * N * 16;
+      const int NB = a.mmaN;
+      const __nv_bfloat16* wsrc = a.w + (size_t)coblk * a.nblk * NB * 16;
       const int total = a.resident ? a.ngroups : a.nchunks * a.ngroups;
       for (int it = 0; it < total; ++it) {
         const int g = it % a.ngroups, stage = it % a.nstages;
@@ -244,9 +246,9 @@ tc_conv_kernel(const KArgs a, const __grid_constant__ CUtensorMap tmap0, const _
           if (!mbar_wait(WEMPTY(stage), ph ^ 1u, a.error_flag, 1)) break;
         }
         const int nb = min(a.G, a.nblk - g * a.G);
-        const uint32_t bytes = (uint32_t)nb * N * 32u;
+        const uint32_t bytes = (uint32_t)nb * NB * 32u;
         mbar_expect_tx(WFULL(stage), bytes);
-        bulk_g2s(smem_u32(w_smem + (size_t)stage * a.w_stage_bytes), wsrc + (size_t)g * a.G * N * 16, bytes,
+        bulk_g2s(smem_u32(w_smem + (size_t)stage * a.w_stage_bytes), wsrc + (size_t)g * a.G * NB * 16, bytes,
                  WFULL(stage));
       }
     }
@@ -256,12 +258,13 @@ tc_conv_kernel(const KArgs a, const __grid_constant__ CUtensorMap tmap0, const _
     // registers with plain R2UR -- no per-MMA election / reconvergence and no waterfall loops.)
     if (elect_one()) {
       // instruction descriptor: D=f32, A=B=bf16, K-major both, N>>3 at [17,23), M>>4 at [24,29)
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+      const int NB = a.mmaN;
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t a_base16 = smem_u32(a_smem) >> 4;
       const uint32_t w_base16 = smem_u32(w_smem) >> 4;
       const uint32_t desc_hi = 8u | (1u << 14);                 // SBO = 128 B, version 1
       const uint32_t a_lbo = ((uint32_t)a.P & 0x3FFFu) << 16;   // next channel group of the brick
-      const uint32_t b_lbo = ((uint32_t)N & 0x3FFFu) << 16;     // next 8 input channels of the filter block
+      const uint32_t b_lbo = ((uint32_t)NB & 0x3FFFu) << 16;    // next 8 input channels of the filter block
       const uint32_t tile_cols = (uint32_t)(a.ncls * N);
       if (a.use_tma) mbar_wait_or_trap(ABAR, 0u, a.error_flag, 5);
       if (tr) a.trace[2] = clock64();
@@ -285,7 +288,7 @@ tc_conv_kernel(const KArgs a, const __grid_constant__ CUtensorMap tmap0, const _
           const uint32_t a_chunk = (a_base16 + (uint32_t)(chunk * a.tpc * 128)) | a_lbo;  // < 2^14 units: no masking
           const uint32_t col_chunk = tmem_base + (uint32_t)(buf * a.cols_per_buf);
 #pragma unroll 2
-          for (int b = g * a.G; b < bend; ++b, b_lo += (uint32_t)(N * 2)) {
+          for (int b = g * a.G; b < bend; ++b, b_lo += (uint32_t)(NB * 2)) {
             const uint2 e = blk_tab[b];
             const uint32_t acc = (e.y >> 31) ? 0u : 1u;
             const uint64_t bdesc = ((uint64_t)desc_hi << 32) | b_lo;
@@ -573,6 +576,7 @@ void tc_free(TcConv* c) {
   if (!c) return;
   free_plans(c->plan_cache);
   ps_free(c);
+  pst_free(c);
   if (c->w) cudaFree(c->w);
   if (c->bias) cudaFree(c->bias);
   delete c;
@@ -676,6 +680,19 @@ int tc_pack(const sgm_conv_desc* m, const sgm_conv_desc* second, int spatial_dim
             c->blocks.push_back(b);
           }
         }
+  } else if (c->ncls * N <= 128 && !getenv("SGM_NO_TFOLD")) {
+    // Transposed conv with few output channels: the parity classes that read the same input shift share one MMA
+    // (N = ncls * Cout columns, zero weights where a class does not use the shift) -- 8 instead of 27 MMAs per 16
+    // input channels; an M=128 K=16 MMA costs ~34 + 0.36 N clk (tests/ubench_mma.cu), so N = 128 is only 2x N = 16.
+    c->tfold = 1;
+    const int np0 = c->flat0 ? 1 : 2;
+    for (int sh0 = 0; sh0 < np0; ++sh0)
+      for (int sh1 = 0; sh1 < 2; ++sh1)
+        for (int sh2 = 0; sh2 < 2; ++sh2)
+          for (int p = 0; p < ncgp; ++p) {
+            KBlock b{0, p, {sh0, sh1, sh2}, 0, c->blocks.empty() ? 1 : 0};
+            c->blocks.push_back(b);
+          }
   } else {
     // o = 2j + p reads in[j + sh] * W[k]:  p=0: (sh 0, k 1);  p=1: (sh 0, k 2), (sh 1, k 0)
     const int np0 = c->flat0 ? 1 : 2;
@@ -696,8 +713,10 @@ int tc_pack(const sgm_conv_desc* m, const sgm_conv_desc* second, int spatial_dim
   }
   const int nblk = (int)c->blocks.size();
 
-  // ---- weights: [coblk][blk][kchunk 2][N][8] bf16
-  std::vector<uint16_t> w((size_t)c->ncoblk * nblk * 2 * N * 8, 0);
+  // ---- weights: [coblk][blk][kchunk 2][N][8] bf16 (class-folded transposed conv: [blk][kchunk 2][cls][N][8])
+  const int NB = c->tfold ? c->ncls * N : N;
+  c->mma_n = NB;
+  std::vector<uint16_t> w((size_t)c->ncoblk * nblk * 2 * NB * 8, 0);
   std::vector<float> bias(c->ntot, 0.f);
   for (int co = 0; co < m->cout; ++co) bias[co] = m->bias[co];
   if (second)
@@ -722,7 +741,32 @@ int tc_pack(const sgm_conv_desc* m, const sgm_conv_desc* second, int spatial_dim
     }
     return (kk[0] * c->k[1] + kk[1]) * c->k[2] + kk[2];
   };
-  for (int cb = 0; cb < c->ncoblk; ++cb)
+  if (c->tfold) {
+    for (int bi = 0; bi < nblk; ++bi) {
+      const KBlock& b = c->blocks[bi];
+      for (int cls = 0; cls < c->ncls; ++cls) {
+        // tap of this class for the block's input shift; a class with parity bit 0 only reads shift 0
+        int kk[3];
+        bool used = true;
+        for (int a = 0; a < 3; ++a) {
+          if (c->k[a] == 1) { kk[a] = 0; continue; }
+          const int pbit = c->flat0 ? (a == 1 ? (cls >> 1) & 1 : (cls & 1)) : (cls >> (2 - a)) & 1;
+          if (pbit == 0) { kk[a] = 1; used = used && b.shift[a] == 0; }
+          else kk[a] = b.shift[a] == 0 ? 2 : 0;
+        }
+        if (!used) continue;
+        const int tap = (kk[0] * c->k[1] + kk[1]) * c->k[2] + kk[2];
+        for (int kc = 0; kc < 2; ++kc)
+          for (int co = 0; co < m->cout; ++co)
+            for (int k8 = 0; k8 < 8; ++k8) {
+              const int ci = (b.cgpair * 2 + kc) * 8 + k8;
+              if (ci >= m->cin) continue;
+              w[(((size_t)bi * 2 + kc) * NB + (cls * N + co)) * 8 + k8] = f2bf(wget(*m, co, ci, tap, ntaps));
+            }
+      }
+    }
+  }
+  for (int cb = 0; cb < c->ncoblk && !c->tfold; ++cb)
     for (int bi = 0; bi < nblk; ++bi) {
       const KBlock& b = c->blocks[bi];
       const int tap = tap_of(b);
@@ -753,7 +797,8 @@ int tc_pack(const sgm_conv_desc* m, const sgm_conv_desc* second, int spatial_dim
     return SGM_ERR_CUDA;
   }
   if (!second) {
-    const int rc = ps_pack(*m, c);
+    int rc = ps_pack(*m, c);
+    if (!rc) rc = pst_pack(*m, c);
     if (rc) {
       tc_free(c);
       return rc;
@@ -854,12 +899,14 @@ static int tc_plan(const TcConv& c, const TcIO& io, KArgs& a, int& smem_bytes_ou
   }
   const int N = c.ncta, nblk = (int)c.blocks.size();
   a.N = N, a.nblk = nblk, a.ncls = c.ncls;
+  const int NB = c.mma_n;
+  a.mmaN = NB;
   // weight ring
-  a.G = std::max(1, std::min(nblk, 16384 / (N * 32)));
+  a.G = std::max(1, std::min(nblk, 16384 / (NB * 32)));
   a.ngroups = ceil_div(nblk, a.G);
-  a.nstages = std::min(a.G * N * 32 <= 8192 ? 6 : 4, a.ngroups);
+  a.nstages = std::min(a.G * NB * 32 <= 8192 ? 6 : 4, a.ngroups);
   a.resident = a.ngroups <= a.nstages;
-  a.w_stage_bytes = round_up(a.G * N * 32, 128);
+  a.w_stage_bytes = round_up(a.G * NB * 32, 128);
   // TMEM
   int cols_tile = c.ncls * N;
   a.nbuf = cols_tile <= 128 ? 2 : 1;
@@ -916,10 +963,10 @@ static int tc_plan(const TcConv& c, const TcIO& io, KArgs& a, int& smem_bytes_ou
         if ((long long)units * 16 + fixed_bytes > kSmemBudget) continue;
         const long long nct = (long long)ceil_div(a.rd[0], t[0]) * ceil_div(a.rd[1], t[1]) * ceil_div(a.rd[2], t[2]) *
                               c.ncoblk * io.n;
-        const double mma = (double)ntl * nblk * (32.0 + N / 4.0);
+        const double mma = (double)ntl * nblk * (34.0 + 0.36 * NB);
         const double load = (double)a.nslab * c.cgin * P * 16 / 24.0;
         const double epi = (double)ntl * c.ncls * (N / 16) * 60.0;
-        const double wload = (double)nblk * N * 32 / 40.0;  // every CTA streams the whole filter bank from L2
+        const double wload = (double)nblk * NB * 32 / 40.0;  // every CTA streams the whole filter bank from L2
         const double cta = std::max(std::max(mma, epi), wload) + load + 4000.0;
         const double waves = (double)((nct + 295) / 296);
         const double cost = waves * cta;
@@ -961,6 +1008,7 @@ int tc_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t
   SGM_REQUIRE(io.cg0 + io.cg1 == c.cgin, SGM_ERR_INVALID, "tc_launch: input channel groups %d+%d != %d", io.cg0,
               io.cg1, c.cgin);
   if (ps_applicable(c, io)) return ps_launch(c, io, error_flag_dev, st);
+  if (pst_applicable(c, io)) return pst_launch(c, io, error_flag_dev, st);
   const int key[8] = {io.id[0], io.id[1], io.id[2], io.od[0], io.od[1], io.od[2], io.n, io.cg0};
   auto* plans = reinterpret_cast<std::vector<PlanEntry>*>(c.plan_cache);
   const PlanEntry* pe = nullptr;

@@ -31,6 +31,8 @@ struct TcConv {
   int k[3] = {3, 3, 3};       // kernel extent per axis (1 on the flat axis of 2-D networks)
   int flat0 = 0;              // 2-D network: axis 0 has extent 1, kernel 1, stride 1
   int ncls = 1;
+  int tfold = 0;              // transposed conv: parity classes folded into the MMA N dimension
+  int mma_n = 0;              // MMA N (ncta, or ncls * ncta when tfold)
   std::vector<KBlock> blocks; // host copy, in weight-pack order
   __nv_bfloat16* w = nullptr; // device [ncoblk][nblk][2][ncta][8]
   float* bias = nullptr;      // device [ntot]
@@ -47,6 +49,11 @@ struct TcConv {
   int ps_cb = 0;                  // columns per d0 tap (4, 8, 10, 16, 20, 24 or 32); 0 = not eligible
   int ps_ncgp = 0;                // input channel pairs of groups (cin padded to 16*ncgp)
   void* ps_plan_cache = nullptr;
+  // transposed plane-sweep packing (conv_pst.cu): stride-2 transposed convs with <= 16 output channels fold the 8
+  // output parity classes into the MMA N dimension
+  __nv_bfloat16* pst_w = nullptr;  // device [8*ncgp][2][128][8], row n' = class*16 + co
+  int pst_ncgp = 0;                // input channel pairs of groups (2 or 4); 0 = not eligible
+  void* pst_plan_cache = nullptr;
 };
 
 struct TcIO {
@@ -88,6 +95,12 @@ int ps_pack(const sgm_conv_desc& d, TcConv* c);          // fills ps_* when the 
 bool ps_applicable(const TcConv& c, const TcIO& io);
 int ps_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t st);
 void ps_free(TcConv* c);
+
+// transposed plane-sweep family (conv_pst.cu)
+int pst_pack(const sgm_conv_desc& d, TcConv* c);
+bool pst_applicable(const TcConv& c, const TcIO& io);
+int pst_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t st);
+void pst_free(TcConv* c);
 
 }  // namespace tc
 }  // namespace sgm
