@@ -76,7 +76,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -276,21 +276,46 @@ def run_b200(args):
         sampler.start()
     for _ in range(max(3, args.warmup)):
         step()
+    # settle: extra untimed steps until two consecutive ones agree within 5 % (allocator growth, clock ramp, the
+    # sampler's NVML start-up); at most 10
+    prev = None
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        cur = e0.elapsed_time(e1)
+        if prev is not None and abs(cur - prev) <= 0.05 * prev:
+            break
+        prev = cur
     net.check()
     barrier()
-    net.set_profiling(not args.no_profile)
-    net.get_profile()
+    # timed region: K steps with NO per-launch instrumentation (an event pair around every launch costs ~30 us of
+    # front-end serialisation per launch, ~20-40 % of a step here)
+    net.set_profiling(False)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]  # one event per step (diagnostic spread)
     barrier()
     sampler.begin()
     ev0.record()
-    for _ in range(args.steps):
+    for i in range(args.steps):
         out = step()
+        marks[i].record()
     ev1.record()
     barrier()
     sampler.end()
     ms = ev0.elapsed_time(ev1) / args.steps
+    per_step = [(ev0 if i == 0 else marks[i - 1]).elapsed_time(marks[i]) for i in range(args.steps)]
     launches_step = net.last_launch_count  # network launches + the gather-blend kernel
+    # per-kernel durations for the rooflines: the same K steps again, with a CUDA-event pair recorded by the
+    # library around every launch on the launching stream
+    net.set_profiling(not args.no_profile)
+    net.get_profile()
+    if not args.no_profile:
+        for _ in range(args.steps):
+            out = step()
+    barrier()
     prof = net.get_profile()
     net.set_profiling(False)
     clocks = sampler.stop() if rank == 0 else None
@@ -314,11 +339,11 @@ def run_b200(args):
         # (data dependent); it is disabled so that e2e runs the same 125 windows as `value`.
         kw = dict(overlap=OVERLAP, mode=MODE, sw_batch_size=args.sw_batch, precision=args.precision,
                   crop_foreground=False)
-        for _ in range(2):
+        for _ in range(3):
             predict_volume(pnet, host, None, (), **kw)
         barrier()
         t0 = time.perf_counter()
-        e2e_steps = max(1, min(args.steps, 5))
+        e2e_steps = max(1, args.steps)
         for _ in range(e2e_steps):
             lab = predict_volume(pnet, host, None, (), **kw)  # returns a HOST uint8 label map
         torch.cuda.synchronize(dev)
@@ -407,6 +432,7 @@ def run_b200(args):
                             parallelism=f"slab{world}" if world > 1 else "single",
                             l2="no flush: per-step working set (67 MB volume + 671 MB accumulator + activations) "
                                "exceeds the 126 MB L2"),
+                step_ms=dict(min=min(per_step), median=float(np.median(per_step)), max=max(per_step)),
                 e2e=e2e, gpu_launches=int(launches_step * args.steps), clocks=clocks, roofline=roofline,
                 roofline_blend=blend_roof,
                 cpu_baseline=cpu,

@@ -51,6 +51,8 @@ struct KArgs {
   int P, nslab;
   int row_first, ntiles, tpc, nchunks, nbuf, ncls, cols_per_buf, tmem_cols;
   int N, nblk, G, ngroups, nstages, resident;
+  int achunk;         // > 0: the brick is streamed in chunks of `achunk` channel groups through a ring (deep layers)
+  int astages, astage_units, nkc;
   int mmaN;           // MMA N: N, or ncls * N when the output parity classes of a transposed conv are folded into one MMA
   int blk_off;        // offset of this conv's K-block descriptors in c_blk
   const __nv_bfloat16* w;
@@ -90,7 +92,9 @@ constexpr int kBlkConst = 12288;
 __constant__ uint32_t c_blk[kBlkConst];
 
 
-__global__ void __launch_bounds__(kThreads, 2)
+// ACH: the brick is streamed in channel chunks (deep layers, one CTA per SM); compiled out of the common path
+template <bool ACH>
+__global__ void __launch_bounds__(kThreads, ACH ? 1 : 2)
 tc_conv_kernel(const KArgs a, const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -110,14 +114,16 @@ tc_conv_kernel(const KArgs a, const __grid_constant__ CUtensorMap tmap0, const _
   uint8_t* w_smem = smem + a_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(w_smem + a.nstages * a.w_stage_bytes);
   // bars: [0,nstages) wfull, [nstages,2nstages) wempty, then tfull[2], tempty[2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * a.nstages + 5);
-  uint2* blk_tab = reinterpret_cast<uint2*>(bars + 2 * a.nstages + 6);  // per K block: {A offset, accumulator column | overwrite}
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * a.nstages + 13);
+  uint2* blk_tab = reinterpret_cast<uint2*>(bars + 2 * a.nstages + 14);  // per K block: {A offset, column | chunk << 16 | overwrite << 31}
   const uint32_t bar0 = smem_u32(bars);
   auto WFULL = [&](int s) { return bar0 + 8u * s; };
   auto WEMPTY = [&](int s) { return bar0 + 8u * (a.nstages + s); };
   auto TFULL = [&](int b) { return bar0 + 8u * (2 * a.nstages + b); };
   auto TEMPTY = [&](int b) { return bar0 + 8u * (2 * a.nstages + 2 + b); };
   const uint32_t ABAR = bar0 + 8u * (2 * a.nstages + 4);  // brick landed (TMA path)
+  auto AFULL = [&](int s) { return bar0 + 8u * (2 * a.nstages + 5 + s); };   // channel-chunk ring (a.achunk > 0)
+  auto AEMPTY = [&](int s) { return bar0 + 8u * (2 * a.nstages + 9 + s); };
 
   if (warp == 4 && lane == 0) {
     for (int s = 0; s < a.nstages; ++s) {
@@ -129,6 +135,10 @@ tc_conv_kernel(const KArgs a, const __grid_constant__ CUtensorMap tmap0, const _
       mbar_init(TEMPTY(b), 128);
     }
     mbar_init(ABAR, 1);
+    for (int st = 0; st < 4; ++st) {
+      mbar_init(AFULL(st), 1);
+      mbar_init(AEMPTY(st), 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 5) {
@@ -191,11 +201,19 @@ tc_conv_kernel(const KArgs a, const __grid_constant__ CUtensorMap tmap0, const _
     const uint32_t d = c_blk[a.blk_off + b];
     const int s0 = (int)(d & 3u) - 1, s1 = (int)((d >> 2) & 3u) - 1, s2 = (int)((d >> 4) & 3u) - 1;
     const int slab = (d >> 6) & 7u, cls = (d >> 9) & 7u, cgpair = (d >> 16) & 0xffu;
-    const int a16 = (slab * a.cgin + cgpair * 2) * a.P + a.row_first + s0 * a.H[1] * a.H[2] + s1 * a.H[2] + s2;
-    blk_tab[b] = make_uint2((uint32_t)a16, (uint32_t)(cls * a.N) | (((d >> 12) & 1u) << 31));
+    int a16 = a.row_first + s0 * a.H[1] * a.H[2] + s1 * a.H[2] + s2;
+    uint32_t kc = 0;
+    if (ACH) {  // offset inside the ring stage of the block's channel chunk
+      const int cpc = a.achunk >> 1;
+      kc = (uint32_t)(cgpair / cpc);
+      a16 += (cgpair % cpc) * 2 * a.P;
+    } else {
+      a16 += (slab * a.cgin + cgpair * 2) * a.P;
+    }
+    blk_tab[b] = make_uint2((uint32_t)a16, (uint32_t)(cls * a.N) | (kc << 16) | (((d >> 12) & 1u) << 31));
   }
   // zero the tail the last M tile may read (keeps garbage rows finite; they are discarded anyway)
-  for (int it = a.nslab * a.cgin * a.P + tid; it < a.a_units; it += kThreads)
+  for (int it = (ACH ? 0 : a.nslab * a.cgin * a.P) + tid; it < a.a_units; it += kThreads)
     *reinterpret_cast<uint4*>(a_smem + (size_t)it * 16) = make_uint4(0, 0, 0, 0);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core reads
   tc_fence_before();
@@ -208,7 +226,7 @@ tc_conv_kernel(const KArgs a, const __grid_constant__ CUtensorMap tmap0, const _
   if (warp == 5) {
     // ================= weight producer: cp.async.bulk ring =================
     if (lane == 0) {
-      if (a.use_tma) {
+      if (a.use_tma && !ACH) {
         // halo brick by TMA: one 4-D box {H2*8 elements, H1, H0, 1 channel group} per group; coordinates may
         // be negative / past the extent -> hardware zero fill == the conv's zero padding at the window border
         mbar_expect_tx(ABAR, (uint32_t)(a.nslab * a.cgin * a.box_bytes));
@@ -266,7 +284,8 @@ tc_conv_kernel(const KArgs a, const __grid_constant__ CUtensorMap tmap0, const _
       const uint32_t a_lbo = ((uint32_t)a.P & 0x3FFFu) << 16;   // next channel group of the brick
       const uint32_t b_lbo = ((uint32_t)NB & 0x3FFFu) << 16;    // next 8 input channels of the filter block
       const uint32_t tile_cols = (uint32_t)(a.ncls * N);
-      if (a.use_tma) mbar_wait_or_trap(ABAR, 0u, a.error_flag, 5);
+      if (a.use_tma && !ACH) mbar_wait_or_trap(ABAR, 0u, a.error_flag, 5);
+      int cur_kc = -1;  // channel chunk whose ring stage the issuer currently reads
       if (tr) a.trace[2] = clock64();
       for (int chunk = 0; chunk < a.nchunks; ++chunk) {
         const int buf = a.nbuf == 2 ? (chunk & 1) : 0;
@@ -285,11 +304,21 @@ tc_conv_kernel(const KArgs a, const __grid_constant__ CUtensorMap tmap0, const _
           }
           const int bend = min(a.nblk, (g + 1) * a.G);
           uint32_t b_lo = (w_base16 + (uint32_t)(stage * a.w_stage_bytes) / 16u) | b_lbo;
-          const uint32_t a_chunk = (a_base16 + (uint32_t)(chunk * a.tpc * 128)) | a_lbo;  // < 2^14 units: no masking
+          uint32_t a_chunk = (a_base16 + (uint32_t)(chunk * a.tpc * 128)) | a_lbo;  // < 2^14 units: no masking
           const uint32_t col_chunk = tmem_base + (uint32_t)(buf * a.cols_per_buf);
 #pragma unroll 2
           for (int b = g * a.G; b < bend; ++b, b_lo += (uint32_t)(NB * 2)) {
             const uint2 e = blk_tab[b];
+            if (ACH) {
+              const int kc = (int)((e.y >> 16) & 0xffu);
+              if (kc != cur_kc) {  // next channel chunk: release the stage just read, wait for the new one
+                if (cur_kc >= 0) tc_commit(AEMPTY(cur_kc % a.astages));
+                mbar_wait_or_trap(AFULL(kc % a.astages), (uint32_t)(kc / a.astages) & 1u, a.error_flag, 6);
+                tc_fence_after();
+                cur_kc = kc;
+              }
+              a_chunk = (a_base16 + (uint32_t)((kc % a.astages) * a.astage_units)) | a_lbo;
+            }
             const uint32_t acc = (e.y >> 31) ? 0u : 1u;
             const uint64_t bdesc = ((uint64_t)desc_hi << 32) | b_lo;
             uint32_t a_lo = a_chunk + e.x;
@@ -310,6 +339,27 @@ tc_conv_kernel(const KArgs a, const __grid_constant__ CUtensorMap tmap0, const _
     // Work items = (tile, class, 16-column piece) of the chunk, walked linearly so that the global
     // residual of item i+1 is in flight while item i is processed.  Identity residuals (up-path
     // residual units and the head: residual == the conv input) come from the shared-memory brick.
+    if (ACH) {
+      // deep layers: the brick does not fit shared memory with all its channels, so it is streamed in chunks of
+      // `achunk` channel groups through a TMA ring while the accumulators of ALL tiles stay in TMEM.  The epilogue
+      // warps idle during the main loop: lane 0 of warp 0 feeds the ring.
+      if (warp == 0 && lane == 0) {
+        const uint32_t a_base = smem_u32(a_smem);
+        const int c0 = org[2] - a.lo[2], c1 = org[1] - a.lo[1], c2 = org[0] - a.lo[0];
+        for (int kc = 0; kc < a.nkc; ++kc) {
+          const int stage = kc % a.astages;
+          if (kc >= a.astages) mbar_wait_or_trap(AEMPTY(stage), (uint32_t)(kc / a.astages - 1) & 1u, a.error_flag, 7);
+          mbar_expect_tx(AFULL(stage), (uint32_t)(a.achunk * a.box_bytes));
+          for (int i = 0; i < a.achunk; ++i) {
+            const int cg = kc * a.achunk + i;
+            const bool first_src = cg < a.cg0;
+            tma_load_4d(a_base + (uint32_t)(stage * a.astage_units + i * a.P) * 16u, first_src ? &tmap0 : &tmap1, c0 * 8, c1,
+                        c2, first_src ? n * a.cg0 + cg : n * a.cg1 + (cg - a.cg0), AFULL(stage));
+          }
+        }
+      }
+      __syncwarp();
+    }
     const long long ovox = (long long)a.od[0] * a.od[1] * a.od[2];
     const int npiece = N / 16;
     bool ok = true;
@@ -648,15 +698,27 @@ int tc_pack(const sgm_conv_desc* m, const sgm_conv_desc* second, int spatial_dim
   c->ncls = tr2 ? (c->flat0 ? 4 : 8) : 1;
   // output channels per CTA: multiple of 16 dividing ntot; TMEM: ncls * N <= 256 columns
   const int cap = tr2 ? std::max(16, 256 / c->ncls) : 128;
+  // deep stride-1 layers run one CTA per (window, column block): 64 columns keep all SMs busy at 6^3
+  const bool deep_s1 = !tr2 && m->stride == 1 && c->cgin >= 16 && c->cgin % 4 == 0 && !c->flat0 && !getenv("SGM_NO_ACHUNK");
   int N = 16;
-  for (int cand = 16; cand <= std::min(cap, c->ntot); cand += 16)
+  for (int cand = 16; cand <= std::min(deep_s1 ? 64 : cap, c->ntot); cand += 16)
     if (c->ntot % cand == 0) N = cand;
   c->ncta = N;
   c->ncoblk = c->ntot / N;
 
   // ---- K blocks
   const int ncgp = c->cgin / 2;
-  if (c->mode == MODE_S1) {
+  c->kmajor = c->mode == MODE_S1 && c->cgin >= 16 && c->cgin % 4 == 0 && !c->flat0 && !getenv("SGM_NO_ACHUNK");
+  if (c->kmajor) {
+    // deep layers (>= 128 input channels): channel-major K blocks, the brick is streamed chunk by chunk (tc_plan)
+    for (int p = 0; p < ncgp; ++p)
+      for (int k0 = 0; k0 < c->k[0]; ++k0)
+        for (int k1 = 0; k1 < c->k[1]; ++k1)
+          for (int k2 = 0; k2 < c->k[2]; ++k2) {
+            KBlock b{0, p, {k0 - c->k[0] / 2, k1 - c->k[1] / 2, k2 - c->k[2] / 2}, 0, c->blocks.empty() ? 1 : 0};
+            c->blocks.push_back(b);
+          }
+  } else if (c->mode == MODE_S1) {
     for (int k0 = 0; k0 < c->k[0]; ++k0)
       for (int k1 = 0; k1 < c->k[1]; ++k1)
         for (int k2 = 0; k2 < c->k[2]; ++k2)
@@ -945,8 +1007,57 @@ static int tc_plan(const TcConv& c, const TcIO& io, KArgs& a, int& smem_bytes_ou
   static const int cand[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64, 96};
   double best = 1e30;
   int bt[3] = {0, 0, 0};
-  const int fixed_bytes = a.nstages * a.w_stage_bytes + (2 * a.nstages + 6) * 8 + nblk * 8 + 16 + 256;
+  const int fixed_bytes = a.nstages * a.w_stage_bytes + (2 * a.nstages + 14) * 8 + nblk * 8 + 16 + 256;
   a.use_tma = tma_available() && !(c.mode == MODE_S2 && getenv("SGM_NO_TMA_S2"));
+  if (c.kmajor) {
+    // ---- chunked-A plan: one CTA per SM, all tiles of the brick accumulate in TMEM at once
+    SGM_REQUIRE(a.use_tma, SGM_ERR_UNSUPPORTED, "deep layers need TMA (cuTensorMapEncodeTiled unavailable)");
+    a.achunk = 4;  // 32 input channels per ring stage
+    a.nkc = c.cgin / a.achunk;
+    a.astages = std::min(3, a.nkc);
+    const int budget = 200 * 1024;
+    for (int c0 : cand)
+      for (int c1 : cand)
+        for (int c2 : cand) {
+          const int t[3] = {std::min(c0, a.rd[0]), std::min(c1, a.rd[1]), std::min(c2, a.rd[2])};
+          const int H[3] = {t[0] + addH[0], t[1] + addH[1], t[2] + addH[2]};
+          const int P = round_up(H[0] * H[1] * H[2], 8);
+          if (P > 4000 || H[2] * 8 > 256 || H[1] > 256 || H[0] > 256) continue;
+          const int rf = (a.lo[0] * H[1] + a.lo[1]) * H[2] + a.lo[2];
+          const int rl = ((a.lo[0] + t[0] - 1) * H[1] + a.lo[1] + t[1] - 1) * H[2] + a.lo[2] + t[2] - 1;
+          const int ntl = ceil_div(rl - rf + 1, 128);
+          if (ntl * N > 512) continue;
+          const int su = round_up(a.achunk * P + 128 + 2 * (H[1] * H[2] + H[2] + 2), 8);
+          if ((long long)a.astages * su * 16 + fixed_bytes > budget) continue;
+          const long long nct = (long long)ceil_div(a.rd[0], t[0]) * ceil_div(a.rd[1], t[1]) * ceil_div(a.rd[2], t[2]) *
+                                c.ncoblk * io.n;
+          const double mma = (double)ntl * nblk * (34.0 + 0.36 * NB);
+          const double cta = mma + 6000.0;
+          const double waves = (double)((nct + 147) / 148);
+          const double cost = waves * cta;
+          if (cost < best) best = cost, bt[0] = t[0], bt[1] = t[1], bt[2] = t[2];
+        }
+    SGM_REQUIRE(bt[0] > 0, SGM_ERR_UNSUPPORTED, "tc_launch: no chunked tile shape fits (cgin=%d, N=%d)", c.cgin, N);
+    for (int i = 0; i < 3; ++i) {
+      a.t[i] = bt[i];
+      a.H[i] = bt[i] + addH[i];
+      a.nt[i] = ceil_div(a.rd[i], bt[i]);
+    }
+    a.P = round_up(a.H[0] * a.H[1] * a.H[2], 8);
+    a.box_bytes = a.H[0] * a.H[1] * a.H[2] * 16;
+    a.row_first = (a.lo[0] * a.H[1] + a.lo[1]) * a.H[2] + a.lo[2];
+    const int row_last = ((a.lo[0] + a.t[0] - 1) * a.H[1] + a.lo[1] + a.t[1] - 1) * a.H[2] + a.lo[2] + a.t[2] - 1;
+    a.ntiles = ceil_div(row_last - a.row_first + 1, 128);
+    a.tpc = a.ntiles, a.nchunks = 1, a.nbuf = 1;
+    a.cols_per_buf = a.ntiles * cols_tile;
+    int pw = 32;
+    while (pw < a.cols_per_buf) pw <<= 1;
+    a.tmem_cols = pw;
+    a.astage_units = round_up(a.achunk * a.P + 128 + 2 * (a.H[1] * a.H[2] + a.H[2] + 2), 8);
+    a.a_units = a.astages * a.astage_units;
+    smem_bytes_out = a.a_units * 16 + fixed_bytes;
+    return SGM_OK;
+  }
   for (int c0 : cand)
     for (int c1 : cand)
       for (int c2 : cand) {
@@ -1032,7 +1143,7 @@ int tc_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t
   a.segA_cg = c.segA_cg, a.actA = c.actA, a.alphaA = c.alphaA;
   a.res = (const __nv_bfloat16*)io.res;
   a.res_mode = 0;
-  if (io.res) a.res_mode = (io.res == io.in0 && c.mode == MODE_S1 && io.in1 == nullptr && io.cgA == c.cgin) ? 2 : 1;
+  if (io.res) a.res_mode = (io.res == io.in0 && c.mode == MODE_S1 && io.in1 == nullptr && io.cgA == c.cgin && !a.achunk) ? 2 : 1;
   a.pl_weighted = io.pl_weighted;
   a.out_kind = io.out_kind, a.pl_out = io.pl_out, a.pl_cstride = io.pl_cstride, a.pl_nstride = io.pl_nstride;
   a.ad0 = io.ad0, a.ad1 = io.ad1, a.ad2 = io.ad2;
@@ -1052,7 +1163,8 @@ int tc_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t
             a.nstages, a.resident, a.a_units, smem_bytes, a.use_tma, a.nt[0] * a.nt[1] * a.nt[2], c.ncoblk, io.n);
   static bool attr_set = false;
   if (!attr_set) {
-    SGM_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    SGM_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    SGM_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   static const bool trace_on = getenv("SGM_TRACE") != nullptr;
@@ -1071,7 +1183,8 @@ int tc_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t
     if (rc) return rc;
   }
   dim3 grid(a.nt[0] * a.nt[1] * a.nt[2], c.ncoblk, io.n);
-  tc_conv_kernel<<<grid, kThreads, smem_bytes, st>>>(a, tm0, tm1);
+  if (a.achunk) tc_conv_kernel<true><<<grid, kThreads, smem_bytes, st>>>(a, tm0, tm1);
+  else tc_conv_kernel<false><<<grid, kThreads, smem_bytes, st>>>(a, tm0, tm1);
   SGM_CUDA_CHECK(cudaGetLastError());
   if (trace_on) {
     long long t[32];

@@ -31,6 +31,7 @@ struct TcConv {
   int k[3] = {3, 3, 3};       // kernel extent per axis (1 on the flat axis of 2-D networks)
   int flat0 = 0;              // 2-D network: axis 0 has extent 1, kernel 1, stride 1
   int ncls = 1;
+  int kmajor = 0;             // deep stride-1 layer: channel-major K blocks, brick streamed in channel chunks
   int tfold = 0;              // transposed conv: parity classes folded into the MMA N dimension
   int mma_n = 0;              // MMA N (ncta, or ncls * ncta when tfold)
   std::vector<KBlock> blocks; // host copy, in weight-pack order
