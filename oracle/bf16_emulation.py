@@ -2,9 +2,10 @@
 
 The bf16 device path (``SGM_PRECISION_BF16``) stores every inter-layer activation in bf16, uses
 BN-folded weights rounded to bf16, keeps biases / PReLU slopes in fp32 and accumulates in fp32; the
-network input (fp32 volume) is rounded to bf16 when the first convolution reads it... except that the
-first (stem) convolution runs on CUDA cores and reads the fp32 volume directly with bf16-rounded
-weights.  This module replays the reference topology (``oracle/unet.py``; reference construction at
+network input (fp32 volume) is rounded to bf16 when the tensor-core stem reads it (3-D networks whose first
+block is a stride-2 k3 conv with 27 * num_channels <= 64 and at most 16 output channels,
+``segmantic_b200/csrc/conv_stem_tc.cu``); every other first block runs on CUDA cores and reads the fp32
+volume directly with bf16-rounded weights.  This module replays the reference topology (``oracle/unet.py``; reference construction at
 ``/root/reference/src/segmantic/seg/monai_unet.py:114-124``) with those rounding points so that the
 tensor-core kernels can be pinned tightly (summation order is then the only difference).
 """
@@ -35,6 +36,12 @@ def _conv(f, x, dims):
     return y
 
 
+def stem_rounds_input(onet) -> bool:
+    """Whether the device path's tensor-core stem (which rounds the network input to bf16) handles this network."""
+    return (onet.dimensions == 3 and onet.strides[0] == 2 and 27 * onet.in_channels <= 64
+            and onet.channels[0] <= 16)
+
+
 def bf16_forward(onet, state_dict, x: torch.Tensor) -> torch.Tensor:
     """Forward of the folded network with bf16 rounding of weights and stored activations."""
     dims = onet.dimensions
@@ -43,6 +50,8 @@ def bf16_forward(onet, state_dict, x: torch.Tensor) -> torch.Tensor:
     n = len(onet.channels) - 1
     it = iter(folded)
     cur = x.to(torch.float32)
+    if stem_rounds_input(onet):
+        cur = _bf(cur)
     skips = []
     for i in range(n + 1):  # n down levels + bottom
         u0, u1, rs = next(it), next(it), next(it)

@@ -80,6 +80,11 @@ int launch_convT_fp32(const ConvArgs& a, bool bf16_storage, cudaStream_t st);
 int stem_cout_tile();
 int launch_stem(const ConvArgs& a, int cgA, int cgB, void* outA, void* outB, bool bf16_storage, cudaStream_t st);
 
+// tensor-core stem (conv_stem_tc.cu): 3-D stride-2 k3 first block with 1-2 input channels, bf16 precision
+int stem_tc_pack(const sgm_conv_desc& u0, const sgm_conv_desc& rs, int spatial_dims, void** w_dev, float** b_dev, int* kp);
+int launch_stem_tc(const ConvArgs& a, const void* w_dev, const float* b_dev, int kp, int cgA, int cgB, void* outA,
+                   void* outB, int* error_flag_dev, cudaStream_t st);
+
 // ---- bf16 tcgen05 family (conv_tc.cu)
 struct TcConvPlan;
 

@@ -51,6 +51,9 @@ struct sgm_unet {
   // with the residual branch), 4 transposed convs, 8 head (conv + blend epilogue)
   float* stem_w = nullptr;     // fused stem: [coblk][tap][ci][STEM_CO] + bias
   float* stem_bias = nullptr;
+  void* stem_tc_w = nullptr;   // tensor-core stem packing (bf16 precision, eligible first blocks only)
+  float* stem_tc_b = nullptr;
+  int stem_tc_kp = 0;
   int tc_mask = 15;
   int* err_dev = nullptr;  // device flag raised by a tcgen05 pipeline timeout
   // optional per-convolution CUDA-event timing (sgm_unet_set_profiling)
@@ -326,7 +329,9 @@ int run_network(sgm_unet* net, const float* vol, long long vol_cstride, int vd1,
         a.vol_cstride = vol_cstride, a.vd1 = vd1, a.vd2 = vd2, a.win_origin = win_origin_dev;
         net->last_launches++;
         Prof prof(net, st, &u0, dry);
-        int rc = launch_stem(a, t.cg, r.cg, t.p, r.p, bf16, st);
+        int rc = (bf16 && net->stem_tc_w)
+                     ? launch_stem_tc(a, net->stem_tc_w, net->stem_tc_b, net->stem_tc_kp, t.cg, r.cg, t.p, r.p, net->err_dev, st)
+                     : launch_stem(a, t.cg, r.cg, t.p, r.p, bf16, st);
         if (rc) return rc;
       }
     } else {
@@ -453,6 +458,8 @@ extern "C" void sgm_unet_destroy(sgm_unet* net) {
   if (net->err_dev) cudaFree(net->err_dev);
   if (net->stem_w) cudaFree(net->stem_w);
   if (net->stem_bias) cudaFree(net->stem_bias);
+  if (net->stem_tc_w) cudaFree(net->stem_tc_w);
+  if (net->stem_tc_b) cudaFree(net->stem_tc_b);
   for (auto& e : net->prof_pending) cudaEventDestroy(e.a), cudaEventDestroy(e.b);
   for (auto& e : net->ev_pool) cudaEventDestroy(e);
   delete net;
@@ -539,6 +546,8 @@ extern "C" int32_t sgm_unet_create(const sgm_unet_desc* d, sgm_unet** out) {
   }
   {
     int rc = pack_stem(d->convs[0], d->convs[2], net->convs[0], net->convs[2], bf16, &net->stem_w, &net->stem_bias);
+    if (!rc && bf16)
+      rc = stem_tc_pack(d->convs[0], d->convs[2], d->spatial_dims, &net->stem_tc_w, &net->stem_tc_b, &net->stem_tc_kp);
     if (rc) {
       sgm_unet_destroy(net);
       return rc;
