@@ -385,18 +385,29 @@ def run_b200(args):
     # Algorithmic work per window: 2*C*C*27*roi^3 FLOP; bytes: read u (C ch, bf16) + write C fp32 logits.
     roofline = None
     if head[2] > 0 and head[1] > 0:
-        per_window_s = head[1] * 1e-3 / (n_win * args.steps)
+        launches = head[2]                      # head launches in the profiled steps (one per window batch)
+        t_launch = head[1] * 1e-3 / launches    # average launch duration, CUDA events on the launching stream
+        wins_per_launch = n_win * args.steps / launches
+        per_window_s = t_launch / wins_per_launch
         head_flop = flops[len(specs) - 1]
-        head_bytes = (esz * CLASSES + 4 * CLASSES) * roi_vox
-        ach = head_flop / per_window_s / 1e12
-        roofline = dict(kernel="tc_conv_kernel[head: conv CxC k3 + identity residual + importance-weighted logits]",
-                        bound="tensor", achieved=ach, peak=pk["bf16_sustained"], unit="TFLOP/s",
-                        frac=ach / pk["bf16_sustained"], traffic=None, peak_source=pk["source"] + " (sustained)",
-                        us_per_window=per_window_s * 1e6, algorithmic_flop_per_window=head_flop,
-                        algorithmic_bytes_per_window=head_bytes, hbm_gbs=head_bytes / per_window_s / 1e9,
-                        hbm_frac=head_bytes / per_window_s / 1e9 / pk["hbm"],
-                        note="N=16 (10 classes padded) MMAs are bound by shared-memory operand bandwidth "
-                             "(4 KB of A per 128x16x16 MMA), not by the dense tensor peak; see DESIGN.md")
+        head_bytes = (esz * CLASSES + 4 * CLASSES) * roi_vox   # read C bf16 channels, write C fp32 weighted logits
+        gbs = head_bytes * wins_per_launch / t_launch / 1e9
+        tfs = head_flop * wins_per_launch / t_launch / 1e12
+        # ncu --set full (profiles/r01b_ncu_top_kernels.md): dram__bytes_read + write of one 32-window launch
+        traffic = 925.79e6 + 1084.31e6 if (CLASSES == 10 and args.precision == "bf16" and args.sw_batch == 32) else None
+        roofline = dict(kernel="ps_conv_kernel<10,1,PLANAR>[head: conv CxC k3 (d0 taps folded into MMA N) + identity "
+                               "residual + importance-weighted fp32 logits]",
+                        bound="hbm", achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=gbs / pk["hbm"],
+                        traffic=traffic, traffic_note="ncu dram bytes of a 32-window launch (algorithmic: 1.70 GB + "
+                                                      "16-channel padding of the bf16 input = 2.04 GB)",
+                        peak_source=pk["source"], us_per_window=per_window_s * 1e6, us_per_launch=t_launch * 1e6,
+                        windows_per_launch=wins_per_launch, algorithmic_bytes_per_window=head_bytes,
+                        algorithmic_bytes_per_launch=head_bytes * wins_per_launch,
+                        algorithmic_flop_per_window=head_flop, tensor_tflops=tfs,
+                        tensor_frac=tfs / pk["bf16_sustained"], tensor_peak=pk["bf16_sustained"],
+                        note="the head moves 60 B per voxel for 5.4 kFLOP: its nearer roof is HBM (fraction above), "
+                             "not the tensor pipe (tensor_frac); SS-mode MMAs with N <= 48 are bound by the shared-memory "
+                             "read of their A tile (tests/ubench_mma.cu), see DESIGN.md 4.1")
     conv_ms = sum(l["ms_per_step"] for l in layers)
     conv_tf = sum(flops.get(i, 0.0) for i in range(len(specs))) * n_win / (conv_ms * 1e-3) / 1e12 if conv_ms else 0.0
 
@@ -410,7 +421,8 @@ def run_b200(args):
             t = blend_prof[1] * 1e-3 / blend_prof[2]
             blend_roof = dict(kernel="gather_blend_cw_kernel[sum covering windows + count + normalise + argmax]",
                               bound="hbm", achieved=blend_bytes / t / 1e9, peak=pk["hbm"], unit="GB/s",
-                              frac=blend_bytes / t / 1e9 / pk["hbm"], traffic=None, peak_source=pk["source"],
+                              frac=blend_bytes / t / 1e9 / pk["hbm"],
+                              traffic=(4423.76e6 + 12.22e6) if CLASSES == 10 else None, peak_source=pk["source"],
                               ms_per_launch=t * 1e3, algorithmic_bytes_per_launch=blend_bytes,
                               formula="4*C*n_windows*roi^3 (weighted logits read once) + 1*V (labels written)")
 

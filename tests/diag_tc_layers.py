@@ -48,9 +48,9 @@ def run_case(net, name, idx, in0, in1=None, res=None, fused=False, cg_out2=0):
         return False
 
 
-def main():
+def run(which="all"):
+    """Runs one group of cases ("s1", "ps", "s2", "t2", "k1", "head" or "all"); returns the list of pass flags."""
     dev = torch.device("cuda:0")
-    which = sys.argv[1] if len(sys.argv) > 1 else "all"
     sd = synthetic_state_dict(3, 1, 10, seed=0)
     net = engine.UNetB200(sd, spatial_dims=3, in_channels=1, out_channels=10, device=dev, precision="bf16")
     results = []
@@ -116,7 +116,8 @@ def main():
         results.append(run_case(net, "t2 64->16 up1 24x16x20 n2", 19, cg8(2, 4, (24, 16, 20), 20, dev), cg8(2, 4, (24, 16, 20), 21, dev)))
         results.append(run_case(net, "t2 32->10 up0 16^3", 21, cg8(1, 2, (16, 16, 16), 22, dev), cg8(1, 2, (16, 16, 16), 23, dev)))
     print(f"SUMMARY {sum(results)}/{len(results)} passed", flush=True)
+    return results
 
 
 if __name__ == "__main__":
-    main()
+    run(sys.argv[1] if len(sys.argv) > 1 else "all")
