@@ -222,7 +222,7 @@ def run_b200(args):
     from segmantic_b200.seg import engine
     from segmantic_b200.seg.monai_unet import Net, predict_volume
     from segmantic_b200.seg.multi_gpu import gather_label_slabs
-    from segmantic_b200.seg.sliding_window import make_schedule, slab_partition
+    from segmantic_b200.seg.sliding_window import make_schedule, slab_partition, window_partition
     from segmantic_b200.seg.unet_spec import unet_conv_specs
     from segmantic_b200.synthetic import synthetic_state_dict
 
@@ -242,7 +242,8 @@ def run_b200(args):
     raw, norm = make_block(seed=1)
     gshape = (VOL[0] * world, VOL[1], VOL[2])
     sched = make_schedule(gshape, ROI, OVERLAP, MODE)
-    all_parts = slab_partition(sched, world)
+    owned = world > 1 and os.environ.get("SGM_MGPU", "owned") != "slab"
+    all_parts = window_partition(sched, world) if owned else slab_partition(sched, world)
     if world > 1:
         part = all_parts[rank]
         # the global volume is the 256^3 block tiled along axis 0; a rank uploads only its halo'ed slab
@@ -251,8 +252,11 @@ def run_b200(args):
     else:
         part = None
         vol_dev = norm.to(dev)
-    n_win = (len(sched.starts[0]) if part is None else part["a0_end"] - part["a0_begin"]) * \
-        len(sched.starts[1]) * len(sched.starts[2])
+    if owned:
+        n_win = part["w_hi"] - part["w_lo"]
+    else:
+        n_win = (len(sched.starts[0]) if part is None else part["a0_end"] - part["a0_begin"]) * \
+            len(sched.starts[1]) * len(sched.starts[2])
     log(f"[rank {rank}] volume {gshape}, {n_win} windows on this rank, precision {args.precision}, "
         f"sw_batch {args.sw_batch}")
 
@@ -261,8 +265,12 @@ def run_b200(args):
             res = engine.sliding_window_inference(vol_dev[None], ROI, args.sw_batch, net, overlap=OVERLAP, mode=MODE,
                                                   return_labels=True, return_logits=False)
             return res["labels"]
-        res = engine.sliding_window_inference_slab(vol_dev, gshape, part, ROI, args.sw_batch, net, overlap=OVERLAP,
-                                                   mode=MODE)
+        if owned:  # every window once; the tail that covers the next rank's planes travels over NVLink
+            res = engine.sliding_window_inference_owned(vol_dev, gshape, part, ROI, args.sw_batch, net, overlap=OVERLAP,
+                                                        mode=MODE, rank=rank, world_size=world)
+        else:
+            res = engine.sliding_window_inference_slab(vol_dev, gshape, part, ROI, args.sw_batch, net, overlap=OVERLAP,
+                                                       mode=MODE)
         # gather the uint8 label slabs on rank 0 (NCCL over NVLink): the only collective of the path
         return gather_label_slabs(res["labels"], all_parts, dst=0)
 
@@ -307,7 +315,7 @@ def run_b200(args):
     sampler.end()
     ms = ev0.elapsed_time(ev1) / args.steps
     per_step = [(ev0 if i == 0 else marks[i - 1]).elapsed_time(marks[i]) for i in range(args.steps)]
-    launches_step = net.last_launch_count  # network launches + the gather-blend kernel
+    launches_step = getattr(net, "last_launch_count_owned", 0) if owned else net.last_launch_count  # network + blend
     # per-kernel durations for the rooflines: the same K steps again, with a CUDA-event pair recorded by the
     # library around every launch on the launching stream
     net.set_profiling(not args.no_profile)
@@ -441,7 +449,7 @@ def run_b200(args):
                                      f"synthetic {gshape[0]}x{gshape[1]}x{gshape[2]} volume, roi 96^3, overlap 0.5, "
                                      "gaussian blend, argmax labels",
                             windows=int(n_win if world == 1 else sched.n_windows), sw_batch=args.sw_batch,
-                            parallelism=f"slab{world}" if world > 1 else "single",
+                            parallelism=(f"owned-windows{world}+p2p-halo" if owned else f"slab{world}") if world > 1 else "single",
                             l2="no flush: per-step working set (67 MB volume + 671 MB accumulator + activations) "
                                "exceeds the 126 MB L2"),
                 step_ms=dict(min=min(per_step), median=float(np.median(per_step)), max=max(per_step)),

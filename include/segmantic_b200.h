@@ -158,6 +158,20 @@ SGM_API int32_t sgm_sw_predict(sgm_unet* net, const float* vol_dev, const sgm_sw
                                uint8_t* labels_dev, float* probs_dev, void* workspace_dev,
                                int64_t workspace_bytes, void* stream);
 
+/* The two halves of sgm_sw_predict as separate calls, for the multi-GPU driver with window OWNERSHIP: a rank
+ * computes the importance-weighted logits of a contiguous range of the schedule's windows (MONAI order, axis 0
+ * slowest) into wl_dev ([w_count][C][roi] fp32), receives the windows of the previous rank that cover its output
+ * planes over NVLink, and blends.  sgm_sw_windows reads cfg->vol_x0 / vol_nx (the input planes present) and
+ * cfg->sw_batch; sgm_sw_blend reads cfg->a0_begin / a0_end (the window rows held in wl_dev, which starts at the
+ * first window of row a0_begin) and cfg->acc_x0 / acc_nx (the output planes).  Same arithmetic as sgm_sw_predict:
+ * bit-identical to the single-device result.  sgm_sw_blend needs 16 KiB of device scratch. */
+SGM_API int64_t sgm_sw_windows_workspace_bytes(const sgm_unet* net, const sgm_sw_cfg* cfg);
+SGM_API int32_t sgm_sw_windows(sgm_unet* net, const float* vol_dev, const sgm_sw_cfg* cfg, int64_t w_first,
+                               int64_t w_count, float* wl_dev, void* workspace_dev, int64_t workspace_bytes,
+                               void* stream);
+SGM_API int32_t sgm_sw_blend(const sgm_sw_cfg* cfg, int32_t channels, const float* wl_dev, float* logits_dev,
+                             uint8_t* labels_dev, float* probs_dev, void* scratch_dev, void* stream);
+
 /* Spacingd / its inverse (seg/monai_unet.py:173-174,615-621): out[c][o] = trilinear(in[c], A*o + t),
  * grid_sample(bilinear, padding border, align_corners False) semantics, float64 arithmetic.
  * xform = row-major 3x4 [A|t] mapping OUTPUT voxel indices to INPUT voxel indices. */

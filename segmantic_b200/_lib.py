@@ -72,6 +72,11 @@ SIGNATURES = {
     "sgm_sw_accumulate": (C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(SwCfg), C.c_void_p, C.c_void_p,
                                       C.c_int64, C.c_void_p]),
     "sgm_sw_workspace_bytes": (C.c_int64, [C.c_void_p, C.POINTER(SwCfg)]),
+    "sgm_sw_windows_workspace_bytes": (C.c_int64, [C.c_void_p, C.POINTER(SwCfg)]),
+    "sgm_sw_windows": (C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(SwCfg), C.c_int64, C.c_int64, C.c_void_p,
+                                   C.c_void_p, C.c_int64, C.c_void_p]),
+    "sgm_sw_blend": (C.c_int32, [C.POINTER(SwCfg), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p]),
     "sgm_sw_predict_workspace_bytes": (C.c_int64, [C.c_void_p, C.POINTER(SwCfg)]),
     "sgm_sw_predict": (C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(SwCfg), C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_int64, C.c_void_p]),

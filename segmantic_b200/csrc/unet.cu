@@ -765,6 +765,92 @@ extern "C" int32_t sgm_sw_predict(sgm_unet* net, const float* vol_dev, const sgm
   return rc;
 }
 
+extern "C" int64_t sgm_sw_windows_workspace_bytes(const sgm_unet* net, const sgm_sw_cfg* cfg) {
+  if (!net || check_cfg(net, cfg)) return SGM_ERR_INVALID;
+  const int B = std::max(1, cfg->sw_batch);
+  const int64_t net_bytes = sgm_unet_workspace_bytes(net, cfg->roi, B);
+  if (net_bytes < 0) return net_bytes;
+  const int64_t nwin = (int64_t)cfg->n_starts[0] * cfg->n_starts[1] * cfg->n_starts[2];
+  return net_bytes + nwin * 3 * (int64_t)sizeof(int) + 3 * 512 * (int64_t)sizeof(float) + 2048;
+}
+
+extern "C" int32_t sgm_sw_windows(sgm_unet* net, const float* vol_dev, const sgm_sw_cfg* cfg, int64_t w_first,
+                                  int64_t w_count, float* wl_dev, void* workspace_dev, int64_t workspace_bytes,
+                                  void* stream) {
+  SGM_REQUIRE(net && vol_dev && wl_dev && workspace_dev, SGM_ERR_INVALID, "sgm_sw_windows: null argument");
+  int rc = check_cfg(net, cfg);
+  if (rc) return rc;
+  const int n1 = cfg->n_starts[1], n2 = cfg->n_starts[2];
+  const int64_t nwin_all = (int64_t)cfg->n_starts[0] * n1 * n2;
+  SGM_REQUIRE(w_first >= 0 && w_count >= 0 && w_first + w_count <= nwin_all, SGM_ERR_INVALID,
+              "sgm_sw_windows: window range [%lld, %lld) outside the schedule's %lld windows", (long long)w_first,
+              (long long)(w_first + w_count), (long long)nwin_all);
+  net->last_launches = 0;
+  if (w_count == 0) return SGM_OK;
+  const int64_t need = sgm_sw_windows_workspace_bytes(net, cfg);
+  SGM_REQUIRE(need >= 0 && workspace_bytes >= need, SGM_ERR_WORKSPACE, "workspace too small: need %lld bytes, got %lld",
+              (long long)need, (long long)workspace_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<int> org_vol;
+  for (int64_t w = w_first; w < w_first + w_count; ++w) {
+    const int a0 = (int)(w / (n1 * n2)), a1 = (int)((w / n2) % n1), a2 = (int)(w % n2);
+    const int s0 = cfg->starts[0][a0];
+    SGM_REQUIRE(s0 >= cfg->vol_x0 && s0 + cfg->roi[0] <= cfg->vol_x0 + cfg->vol_nx, SGM_ERR_INVALID,
+                "window start %d needs planes outside vol_dev [%d,%d)", s0, cfg->vol_x0, cfg->vol_x0 + cfg->vol_nx);
+    org_vol.push_back(s0 - cfg->vol_x0), org_vol.push_back(cfg->starts[1][a1]), org_vol.push_back(cfg->starts[2][a2]);
+  }
+  const int nwin = (int)w_count;
+  Bump ws{(char*)workspace_dev, workspace_bytes, 0, false};
+  int* org_dev = (int*)ws.take((int64_t)nwin * 3 * sizeof(int));
+  float* imap_dev = (float*)ws.take(3 * 512 * sizeof(float));
+  SGM_CUDA_CHECK(cudaMemcpyAsync(org_dev, org_vol.data(), org_vol.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  for (int a = 0; a < 3; ++a)
+    SGM_CUDA_CHECK(cudaMemcpyAsync(imap_dev + a * 512, cfg->imap[a], cfg->roi[a] * sizeof(float),
+                                   cudaMemcpyHostToDevice, st));
+  // (pageable sources: cudaMemcpyAsync has staged them when it returns)
+  const int B = std::max(1, std::min(cfg->sw_batch, nwin));
+  const long long plane = (long long)cfg->dims[1] * cfg->dims[2];
+  const long long roivox = (long long)cfg->roi[0] * cfg->roi[1] * cfg->roi[2];
+  HeadTarget head;
+  memset(&head, 0, sizeof(head));
+  head.kind = OUT_PLANAR, head.weighted = 1;
+  head.cstride = roivox, head.nstride = roivox * net->cout;
+  for (int a = 0; a < 3; ++a) head.imap[a] = imap_dev + a * 512;
+  head.floor = cfg->imap_floor;
+  const int64_t ws_mark = ws.off;
+  int64_t launches = 0;
+  for (int w0 = 0; w0 < nwin; w0 += B) {
+    const int nb = std::min(B, nwin - w0);
+    ws.off = ws_mark;
+    head.out = wl_dev + (size_t)w0 * net->cout * roivox;
+    rc = run_network(net, vol_dev, (long long)cfg->vol_nx * plane, cfg->dims[1], cfg->dims[2],
+                     org_dev + (size_t)w0 * 3, nb, cfg->roi, ws, head, st, false);
+    if (rc) return rc;
+    launches += net->last_launches;
+    net->last_launches = 0;
+  }
+  net->last_launches = launches;
+  return SGM_OK;
+}
+
+extern "C" int32_t sgm_sw_blend(const sgm_sw_cfg* cfg, int32_t channels, const float* wl_dev, float* logits_dev,
+                                uint8_t* labels_dev, float* probs_dev, void* scratch_dev, void* stream) {
+  SGM_REQUIRE(wl_dev && scratch_dev && channels >= 1, SGM_ERR_INVALID, "sgm_sw_blend: bad argument");
+  int rc = check_cfg(nullptr, cfg);
+  if (rc) return rc;
+  SGM_REQUIRE(cfg->a0_begin >= 0 && cfg->a0_end <= cfg->n_starts[0] && cfg->a0_begin < cfg->a0_end, SGM_ERR_INVALID,
+              "bad axis-0 start range");
+  cudaStream_t st = (cudaStream_t)stream;
+  int* starts_dev = (int*)scratch_dev;                                   // 3 * SGM_MAX_STARTS ints
+  float* imap_dev = (float*)((char*)scratch_dev + 3 * SGM_MAX_STARTS * sizeof(int) + 256);
+  SGM_CUDA_CHECK(cudaMemcpyAsync(starts_dev, cfg->starts, 3 * SGM_MAX_STARTS * sizeof(int), cudaMemcpyHostToDevice, st));
+  for (int a = 0; a < 3; ++a)
+    SGM_CUDA_CHECK(cudaMemcpyAsync(imap_dev + a * 512, cfg->imap[a], cfg->roi[a] * sizeof(float),
+                                   cudaMemcpyHostToDevice, st));
+  const float* imaps[3] = {imap_dev, imap_dev + 512, imap_dev + 1024};
+  return launch_gather_blend(wl_dev, channels, cfg, starts_dev, imaps, logits_dev, labels_dev, probs_dev, st);
+}
+
 namespace {
 __constant__ int c_starts[3 * SGM_MAX_STARTS];
 __constant__ float c_imap[3 * 512];

@@ -112,6 +112,15 @@ class UNetB200:
             self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
         return self._ws
 
+    def _buffer(self, name: str, nelem: int) -> torch.Tensor:
+        """Cached float32 device buffer (grown on demand) for the multi-GPU window exchange."""
+        bufs = self.__dict__.setdefault("_bufs", {})
+        b = bufs.get(name)
+        if b is None or b.numel() < nelem:
+            bufs[name] = None
+            b = bufs[name] = torch.empty(int(nelem), dtype=torch.float32, device=self.device)
+        return b
+
     @property
     def last_launch_count(self) -> int:
         return int(self._lib.sgm_unet_last_launch_count(self._handle))
@@ -337,6 +346,114 @@ def sliding_window_inference_slab(vol_slab: torch.Tensor, global_size: Sequence[
     out = {"labels": labels}
     if logits is not None:
         out["logits"] = logits
+    return out
+
+
+class OwnedWindows:
+    """One rank's share of a window-ownership run (``sliding_window.window_partition``), in three steps so that the
+    exchange can be NCCL point-to-point (``sliding_window_inference_owned``) or, in the single-GPU test, a plain copy
+    between two simulated ranks: ``compute_tail()`` (the windows the next rank also needs) -> send ``send_view`` /
+    receive into ``recv_view`` -> ``compute_rest()`` -> ``blend()``."""
+
+    def __init__(self, vol_slab: torch.Tensor, global_size: Sequence[int], part: dict, roi_size: Sequence[int],
+                 sw_batch_size: int, net: UNetB200, overlap: float, mode: str, sigma_scale: float = 0.125,
+                 tag: str = ""):
+        size3 = tuple(int(s) for s in global_size)
+        sched = make_schedule(size3, net.roi3(roi_size), overlap, mode, sigma_scale)
+        if sched.padded_size != size3:
+            raise ValueError("owned-window execution needs a volume at least as large as the roi along every axis")
+        self.net, self.sched, self.part = net, sched, part
+        self.w_lo, self.w_hi, self.wb, self.send_lo = (int(part[k]) for k in ("w_lo", "w_hi", "wb", "send_lo"))
+        vol_nx = int(part["vol_x1"]) - int(part["vol_x0"])
+        if tuple(vol_slab.shape) != (net.in_channels, vol_nx, size3[1], size3[2]):
+            raise ValueError(f"vol_slab must be {(net.in_channels, vol_nx, size3[1], size3[2])}, got {tuple(vol_slab.shape)}")
+        self.vol = vol_slab.contiguous()
+        roivox = int(sched.roi[0]) * int(sched.roi[1]) * int(sched.roi[2])
+        self.stride = net.out_channels * roivox
+        self.nx = int(part["x1"]) - int(part["x0"])
+        self.plane = (size3[1], size3[2])
+        device_batch = max(int(sw_batch_size), int(os.environ.get("SGM_SW_BATCH", DEVICE_SW_BATCH)))
+        self.cfg, self._keep = _make_cfg(
+            sched, device_batch, (int(part["b_begin"]), max(int(part["b_end"]), int(part["b_begin"]))),
+            (int(part["vol_x0"]), max(vol_nx, 1)), (int(part["x0"]) if self.nx > 0 else 0, max(self.nx, 1)))
+        # weighted logits of windows [wb, w_hi): the received part first, the own windows after it
+        self.wl = net._buffer("wl" + tag, max(self.w_hi - self.wb, 1) * self.stride)
+        self.launches = 0
+
+    @property
+    def recv_view(self) -> torch.Tensor:
+        return self.wl[: (self.w_lo - self.wb) * self.stride]
+
+    @property
+    def send_view(self) -> torch.Tensor:
+        return self.wl[(self.send_lo - self.wb) * self.stride: (self.w_hi - self.wb) * self.stride]
+
+    def _compute(self, first: int, count: int):
+        if count <= 0:
+            return
+        net, lib = self.net, self.net._lib
+        with torch.cuda.device(net.device):
+            need = lib.sgm_sw_windows_workspace_bytes(net._handle, C.byref(self.cfg))
+            _lib.check(need, "sgm_sw_windows_workspace_bytes")
+            ws = net._workspace(need)
+            off = (first - self.wb) * self.stride
+            _lib.check(lib.sgm_sw_windows(net._handle, self.vol.data_ptr(), C.byref(self.cfg), first, count,
+                                          self.wl[off:].data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(net.device)),
+                       "sgm_sw_windows")
+            self.launches += int(lib.sgm_unet_last_launch_count(net._handle))
+
+    def compute_tail(self):
+        self._compute(self.send_lo, self.w_hi - self.send_lo)
+
+    def compute_rest(self):
+        self._compute(self.w_lo, self.send_lo - self.w_lo)
+
+    def blend(self, return_logits: bool = False):
+        net, lib, sched = self.net, self.net._lib, self.sched
+        C_out = net.out_channels
+        logits = None
+        if self.nx <= 0:
+            return {"labels": torch.empty((0,) + self.plane, dtype=torch.uint8, device=net.device)}
+        with torch.cuda.device(net.device):
+            if return_logits:
+                logits = torch.empty((C_out, self.nx) + self.plane, dtype=torch.float32, device=net.device)
+            labels = torch.empty((self.nx,) + self.plane, dtype=torch.uint8, device=net.device)
+            scratch = net._buffer("blend_scratch", 4096)
+            per_row = len(sched.starts[1]) * len(sched.starts[2])
+            wl_rows = self.wl[(int(self.part["b_begin"]) * per_row - self.wb) * self.stride:]
+            _lib.check(lib.sgm_sw_blend(C.byref(self.cfg), C_out, wl_rows.data_ptr(),
+                                        logits.data_ptr() if logits is not None else None, labels.data_ptr(), None,
+                                        scratch.data_ptr(), _stream_ptr(net.device)), "sgm_sw_blend")
+        self.launches += 1
+        out = {"labels": labels}
+        if logits is not None:
+            out["logits"] = logits
+        return out
+
+
+def sliding_window_inference_owned(vol_slab: torch.Tensor, global_size: Sequence[int], part: dict,
+                                   roi_size: Sequence[int], sw_batch_size: int, predictor: UNetB200,
+                                   overlap: float = 0.25, mode: str = "constant", sigma_scale: float = 0.125,
+                                   *, rank: int = 0, world_size: int = 1, group=None, return_logits: bool = False):
+    """Multi-GPU form with window OWNERSHIP (``sliding_window.window_partition``): this rank computes the
+    importance-weighted logits of its own windows only, sends the tail that also covers the next rank's planes
+    over NVLink (NCCL point-to-point), receives the corresponding tail of the previous rank, and blends its output
+    planes ``[part.x0, part.x1)`` in MONAI's window order -- bit-identical to the single-device result, and no
+    window is computed twice.  ``vol_slab``: ``[Cin, part.vol_x1 - part.vol_x0, Y, Z]`` float32 on the device."""
+    import torch.distributed as dist
+
+    run = OwnedWindows(vol_slab, global_size, part, roi_size, sw_batch_size, predictor, overlap, mode, sigma_scale)
+    reqs = []
+    if rank > 0 and run.recv_view.numel() > 0:
+        reqs.append(dist.irecv(run.recv_view, src=rank - 1, group=group))
+    run.compute_tail()  # the tail the next rank waits for goes first; it travels while the rest is computed
+    if rank + 1 < world_size and run.send_view.numel() > 0:
+        reqs.append(dist.isend(run.send_view, dst=rank + 1, group=group))
+    run.compute_rest()
+    for r in reqs:
+        r.wait()
+    out = run.blend(return_logits)
+    predictor.last_launch_count_owned = run.launches
     return out
 
 

@@ -15,7 +15,7 @@ from typing import Callable, List, Optional, Sequence
 import torch
 import torch.distributed as dist
 
-from .sliding_window import Schedule, make_schedule, slab_partition
+from .sliding_window import Schedule, make_schedule, slab_partition, window_partition
 
 
 def rank_slab(global_size: Sequence[int], roi: Sequence[int], overlap: float, mode: str, rank: int,
@@ -23,6 +23,17 @@ def rank_slab(global_size: Sequence[int], roi: Sequence[int], overlap: float, mo
     """(schedule, all slabs, this rank's slab) for a volume that is at least ROI-sized everywhere."""
     sched = make_schedule(tuple(global_size), tuple(roi), overlap, mode, sigma_scale)
     parts = slab_partition(sched, world_size)
+    return sched, parts, parts[rank]
+
+
+def rank_windows(global_size: Sequence[int], roi: Sequence[int], overlap: float, mode: str, rank: int,
+                 world_size: int, sigma_scale: float = 0.125):
+    """(schedule, all parts, this rank's part) of the window-ownership partition (``window_partition``): every
+    window is computed once; a rank receives the windows of rank-1 that cover its planes (NCCL point-to-point over
+    NVLink) -- the near-linear form of the driver.  Falls back to ``slab_partition`` semantics via ``rank_slab``
+    when a rank would need windows of two earlier ranks."""
+    sched = make_schedule(tuple(global_size), tuple(roi), overlap, mode, sigma_scale)
+    parts = window_partition(sched, world_size)
     return sched, parts, parts[rank]
 
 

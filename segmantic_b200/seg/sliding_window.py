@@ -136,3 +136,62 @@ def slab_partition(schedule: Schedule, world_size: int) -> List[dict]:
             vx0 = vx1 = x0
         parts.append(dict(x0=x0, x1=x1, a0_begin=a0b, a0_end=a0e, vol_x0=vx0, vol_x1=vx1))
     return parts
+
+
+def window_partition(schedule: Schedule, world_size: int) -> List[dict]:
+    """Partition the window LIST (MONAI order, axis 0 slowest) evenly over `world_size` ranks (multi-GPU
+    driver, near-linear form: no window is computed twice).
+
+    Rank r owns the contiguous windows ``[w_lo, w_hi)`` and the output planes ``[x0, x1)`` that start at the
+    window row holding ``w_lo``.  Its planes are also covered by windows of earlier rows, which rank r-1 owns:
+    they form the contiguous range ``[wb, w_lo)`` (``wb`` = first window of the first row that intersects the
+    planes) and are RECEIVED from rank r-1; symmetrically rank r SENDS the tail ``[send_lo, w_hi)`` of its own
+    range to rank r+1.  Blending rows ``[b_begin, b_end)`` in window order then reproduces the single-device
+    sequence of fp32 additions for every voxel.  Per rank: ``dict(w_lo, w_hi, x0, x1, b_begin, b_end, wb,
+    send_lo, vol_x0, vol_x1)``; ranks beyond the number of windows get empty ranges.
+    """
+    s0 = schedule.starts[0]
+    n0, roi0, size0 = len(s0), schedule.roi[0], schedule.padded_size[0]
+    per_row = len(schedule.starts[1]) * len(schedule.starts[2])
+    total = n0 * per_row
+    world_size = max(1, int(world_size))
+    bounds = [(total * r) // world_size for r in range(world_size + 1)]
+    parts = []
+    for r in range(world_size):
+        w_lo, w_hi = bounds[r], bounds[r + 1]
+        if w_hi <= w_lo:
+            parts.append(dict(w_lo=w_lo, w_hi=w_lo, x0=size0, x1=size0, b_begin=0, b_end=0, wb=w_lo, send_lo=w_lo,
+                              vol_x0=0, vol_x1=0))
+            continue
+        row_lo, row_hi = w_lo // per_row, (w_hi - 1) // per_row
+        x0 = 0 if r == 0 else s0[row_lo]
+        parts.append(dict(w_lo=w_lo, w_hi=w_hi, x0=x0, x1=size0, row_lo=row_lo, row_hi=row_hi,
+                          vol_x0=s0[row_lo], vol_x1=s0[row_hi] + roi0))
+    # a rank's planes end where the next non-empty rank's begin
+    nxt = size0
+    for r in range(world_size - 1, -1, -1):
+        p = parts[r]
+        if p["w_hi"] <= p["w_lo"]:
+            continue
+        p["x1"] = nxt
+        nxt = p["x0"]
+    for r, p in enumerate(parts):
+        if p["w_hi"] <= p["w_lo"]:
+            continue
+        if p["x1"] <= p["x0"]:  # all of its windows sit in a row shared with the previous rank: nothing to blend
+            p.update(b_begin=0, b_end=0, wb=p["w_lo"])
+        else:
+            rows = [j for j in range(n0) if s0[j] < p["x1"] and s0[j] + roi0 > p["x0"]]
+            p.update(b_begin=rows[0], b_end=rows[-1] + 1, wb=min(rows[0] * per_row, p["w_lo"]))
+        p.pop("row_lo", None), p.pop("row_hi", None)
+    for r, p in enumerate(parts):
+        nxt_wb = None
+        for q in parts[r + 1:]:
+            if q["w_hi"] > q["w_lo"]:
+                nxt_wb = q["wb"]
+                break
+        p["send_lo"] = p["w_hi"] if nxt_wb is None else min(max(nxt_wb, p["w_lo"]), p["w_hi"])
+        if nxt_wb is not None and nxt_wb < p["w_lo"]:
+            raise ValueError("window_partition: a rank would need windows of two earlier ranks "
+                             f"(world_size {world_size} too large for {n0} window rows); use slab_partition")
+    return parts

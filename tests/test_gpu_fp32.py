@@ -131,3 +131,33 @@ def test_slab_partition_is_bit_identical(cuda_device):
         logits = torch.cat([eng.sliding_window_inference(vol, roi, 4, net, overlap=0.5, mode="gaussian", slab=p)
                             for p in parts], dim=2)
         assert torch.equal(logits, full["logits"]), f"world={world}"
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_window_ownership_is_bit_identical(cuda_device, precision):
+    """The near-linear multi-GPU form on ONE device: ranks are simulated one after the other and the NVLink
+    exchange is a plain copy.  Every window is computed once; each rank's planes equal the single-device run."""
+    eng = _engine()
+    from segmantic_b200.seg.sliding_window import make_schedule, window_partition
+    onet, sd = make_oracle_net(3, 1, 4, seed=5)
+    vol = normalized_volume((150, 48, 64), seed=3)[None].to(cuda_device)
+    roi = (32, 32, 32)
+    net = eng.UNetB200(sd, spatial_dims=3, in_channels=1, out_channels=4, device=cuda_device, precision=precision)
+    full = eng.sliding_window_inference(vol, roi, 4, net, overlap=0.5, mode="gaussian", return_labels=True)
+    sched = make_schedule(vol.shape[2:], roi, 0.5, "gaussian")
+    for world in (2, 3, 4):
+        parts = window_partition(sched, world)
+        runs = [eng.OwnedWindows(vol[0, :, p["vol_x0"]:p["vol_x1"]], vol.shape[2:], p, roi, 4, net, 0.5, "gaussian",
+                                 tag=str(r)) for r, p in enumerate(parts)]
+        assert sum(p["w_hi"] - p["w_lo"] for p in parts) == sched.n_windows
+        for r, run in enumerate(runs):
+            run.compute_tail()
+            run.compute_rest()
+            if r + 1 < world and run.send_view.numel():
+                assert runs[r + 1].recv_view.numel() == run.send_view.numel()
+                runs[r + 1].recv_view.copy_(run.send_view)  # stands in for isend / irecv
+        outs = [run.blend(return_logits=True) for run in runs]
+        logits = torch.cat([o["logits"] for o in outs if "logits" in o], dim=1)
+        labels = torch.cat([o["labels"] for o in outs], dim=0)
+        assert torch.equal(logits, full["logits"][0]), f"world={world}"
+        assert torch.equal(labels, full["labels"][0, 0]), f"world={world}"
