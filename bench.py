@@ -242,7 +242,22 @@ def run_b200(args):
     raw, norm = make_block(seed=1)
     gshape = (VOL[0] * world, VOL[1], VOL[2])
     sched = make_schedule(gshape, ROI, OVERLAP, MODE)
-    owned = world > 1 and os.environ.get("SGM_MGPU", "owned") != "slab"
+    # N > 1: output slabs with ROI halos (default: no data-path collective at all) or, with SGM_MGPU=owned, window
+    # ownership + one NVLink point-to-point exchange per seam (faster: 2292 vs 2166 Mvoxel/s at N = 2, 3877 at N = 4;
+    # opt-in because one of six back-to-back 2-GPU runs stalled inside NCCL on this pool)
+    owned = world > 1 and os.environ.get("SGM_MGPU", "slab") == "owned"
+    seam_groups = None
+    if owned:
+        # two extra communicators: a rank's receive (from rank-1) and send (to rank+1) must not share one; their
+        # pairwise NCCL communicators are created here, outside the timed steps
+        seam_groups = (dist.new_group(), dist.new_group())
+        token = torch.zeros(1, device=dev)
+        for s_ in range(world - 1):
+            if rank == s_:
+                dist.send(token, dst=s_ + 1, group=seam_groups[s_ % 2])
+            elif rank == s_ + 1:
+                dist.recv(token, src=s_, group=seam_groups[s_ % 2])
+        dist.barrier()
     all_parts = window_partition(sched, world) if owned else slab_partition(sched, world)
     if world > 1:
         part = all_parts[rank]
@@ -267,7 +282,7 @@ def run_b200(args):
             return res["labels"]
         if owned:  # every window once; the tail that covers the next rank's planes travels over NVLink
             res = engine.sliding_window_inference_owned(vol_dev, gshape, part, ROI, args.sw_batch, net, overlap=OVERLAP,
-                                                        mode=MODE, rank=rank, world_size=world)
+                                                        mode=MODE, rank=rank, world_size=world, group=seam_groups)
         else:
             res = engine.sliding_window_inference_slab(vol_dev, gshape, part, ROI, args.sw_batch, net, overlap=OVERLAP,
                                                        mode=MODE)

@@ -297,6 +297,9 @@ int sm_count() {
     int dev = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    // multi-GPU runs leave a few SMs to the NCCL point-to-point kernels of the seam exchange: a persistent grid of
+    // one CTA per SM would otherwise need a second wave whenever NCCL holds an SM
+    if (const char* env = getenv("SGM_RESERVE_SMS")) n = std::max(8, n - atoi(env));
   }
   return n;
 }

@@ -442,13 +442,17 @@ def sliding_window_inference_owned(vol_slab: torch.Tensor, global_size: Sequence
     window is computed twice.  ``vol_slab``: ``[Cin, part.vol_x1 - part.vol_x0, Y, Z]`` float32 on the device."""
     import torch.distributed as dist
 
+    # `group` may be a pair of process groups: the seam between ranks s and s+1 then uses group[s % 2], so that a
+    # rank's receive (seam rank-1) and send (seam rank) live on different NCCL communicators.  On ONE communicator
+    # unbatched point-to-point operations are serialised in posting order, which chains the seams across the ranks.
+    seam_group = (lambda s: group[s % 2]) if isinstance(group, (tuple, list)) else (lambda s: group)
     run = OwnedWindows(vol_slab, global_size, part, roi_size, sw_batch_size, predictor, overlap, mode, sigma_scale)
     reqs = []
     if rank > 0 and run.recv_view.numel() > 0:
-        reqs.append(dist.irecv(run.recv_view, src=rank - 1, group=group))
+        reqs.append(dist.irecv(run.recv_view, src=rank - 1, group=seam_group(rank - 1)))
     run.compute_tail()  # the tail the next rank waits for goes first; it travels while the rest is computed
     if rank + 1 < world_size and run.send_view.numel() > 0:
-        reqs.append(dist.isend(run.send_view, dst=rank + 1, group=group))
+        reqs.append(dist.isend(run.send_view, dst=rank + 1, group=seam_group(rank)))
     run.compute_rest()
     for r in reqs:
         r.wait()
