@@ -699,17 +699,31 @@ int tc_pack(const sgm_conv_desc* m, const sgm_conv_desc* second, int spatial_dim
   // output channels per CTA: multiple of 16 dividing ntot; TMEM: ncls * N <= 256 columns
   const int cap = tr2 ? std::max(16, 256 / c->ncls) : 128;
   // deep stride-1 layers run one CTA per (window, column block): 64 columns keep all SMs busy at 6^3
-  const bool deep_s1 = !tr2 && m->stride == 1 && c->cgin >= 16 && c->cgin % 4 == 0 && !c->flat0 && !getenv("SGM_NO_ACHUNK");
+  const bool deep = c->cgin >= 16 && c->cgin % 4 == 0 && !c->flat0 && !getenv("SGM_NO_ACHUNK");
+  const bool deep_s1 = deep && !tr2 && m->stride == 1;
+  // deep transposed layers: 8 classes x 16 columns x 3 tiles of the 7^3 brick = 384 TMEM columns, all resident
+  const bool deep_t2 = deep && tr2 && c->cgin >= 32 && !getenv("SGM_NO_ACHUNK_T2");
   int N = 16;
-  for (int cand = 16; cand <= std::min(deep_s1 ? 64 : cap, c->ntot); cand += 16)
+  for (int cand = 16; cand <= std::min(deep_s1 ? 64 : (deep_t2 ? 16 : cap), c->ntot); cand += 16)
     if (c->ntot % cand == 0) N = cand;
   c->ncta = N;
   c->ncoblk = c->ntot / N;
 
   // ---- K blocks
   const int ncgp = c->cgin / 2;
-  c->kmajor = c->mode == MODE_S1 && c->cgin >= 16 && c->cgin % 4 == 0 && !c->flat0 && !getenv("SGM_NO_ACHUNK");
-  if (c->kmajor) {
+  c->kmajor = deep_s1 || deep_t2;
+  if (deep_t2) {
+    // channel-major K blocks of the class-folded transposed conv: (cgpair, input shift), all 8 parity classes of
+    // the CTA's 16 output channels in one MMA (N = 128, zero weights where a class does not read the shift)
+    c->tfold = 1;
+    for (int p = 0; p < ncgp; ++p)
+      for (int sh0 = 0; sh0 < 2; ++sh0)
+        for (int sh1 = 0; sh1 < 2; ++sh1)
+          for (int sh2 = 0; sh2 < 2; ++sh2) {
+            KBlock b{0, p, {sh0, sh1, sh2}, 0, c->blocks.empty() ? 1 : 0};
+            c->blocks.push_back(b);
+          }
+  } else if (c->kmajor) {
     // deep layers (>= 128 input channels): channel-major K blocks, the brick is streamed chunk by chunk (tc_plan)
     for (int p = 0; p < ncgp; ++p)
       for (int k0 = 0; k0 < c->k[0]; ++k0)
@@ -803,7 +817,7 @@ int tc_pack(const sgm_conv_desc* m, const sgm_conv_desc* second, int spatial_dim
     }
     return (kk[0] * c->k[1] + kk[1]) * c->k[2] + kk[2];
   };
-  if (c->tfold) {
+  for (int cb = 0; cb < c->ncoblk && c->tfold; ++cb) {
     for (int bi = 0; bi < nblk; ++bi) {
       const KBlock& b = c->blocks[bi];
       for (int cls = 0; cls < c->ncls; ++cls) {
@@ -819,12 +833,15 @@ int tc_pack(const sgm_conv_desc* m, const sgm_conv_desc* second, int spatial_dim
         if (!used) continue;
         const int tap = (kk[0] * c->k[1] + kk[1]) * c->k[2] + kk[2];
         for (int kc = 0; kc < 2; ++kc)
-          for (int co = 0; co < m->cout; ++co)
+          for (int nn = 0; nn < N; ++nn) {
+            const int co = cb * N + nn;
+            if (co >= m->cout) continue;
             for (int k8 = 0; k8 < 8; ++k8) {
               const int ci = (b.cgpair * 2 + kc) * 8 + k8;
               if (ci >= m->cin) continue;
-              w[(((size_t)bi * 2 + kc) * NB + (cls * N + co)) * 8 + k8] = f2bf(wget(*m, co, ci, tap, ntaps));
+              w[((((size_t)cb * nblk + bi) * 2 + kc) * NB + (cls * N + nn)) * 8 + k8] = f2bf(wget(*m, co, ci, tap, ntaps));
             }
+          }
       }
     }
   }
@@ -1026,7 +1043,7 @@ static int tc_plan(const TcConv& c, const TcIO& io, KArgs& a, int& smem_bytes_ou
           const int rf = (a.lo[0] * H[1] + a.lo[1]) * H[2] + a.lo[2];
           const int rl = ((a.lo[0] + t[0] - 1) * H[1] + a.lo[1] + t[1] - 1) * H[2] + a.lo[2] + t[2] - 1;
           const int ntl = ceil_div(rl - rf + 1, 128);
-          if (ntl * N > 512) continue;
+          if (ntl * cols_tile > 512) continue;  // all tiles (x parity classes) stay resident in TMEM
           const int su = round_up(a.achunk * P + 128 + 2 * (H[1] * H[2] + H[2] + 2), 8);
           if ((long long)a.astages * su * 16 + fixed_bytes > budget) continue;
           const long long nct = (long long)ceil_div(a.rd[0], t[0]) * ceil_div(a.rd[1], t[1]) * ceil_div(a.rd[2], t[2]) *
