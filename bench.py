@@ -59,21 +59,36 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.
+    """SM clock / throttle reasons sampled DURING the timed region.
 
-    The nvidia-smi process is started well before the timed region (its NVML start-up can take hundreds of
-    milliseconds and perturbs concurrent launches); only the rows that arrive between begin() and end()
-    are reported."""
+    NVML through `pynvml` in a polling thread (started well before the timed region; every nvidia-smi query spawned
+    alongside the timed loop cost an occasional 10 ms stall of the launch stream), falling back to an `nvidia-smi
+    -lms` child process.  Only the samples taken between begin() and end() are reported."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    PERIOD = 0.02
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml = index, [], None, None
         self.t0 = self.t1 = None
+        self._stop = False
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception as e:  # noqa: BLE001
+            log("pynvml unavailable, using nvidia-smi:", e)
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "50"],
@@ -86,6 +101,25 @@ class ClockSampler:
         except Exception as e:  # noqa: BLE001
             log("clock sampler unavailable:", e)
 
+    def _poll(self):
+        n = self.nvml
+        names = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                 ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                 ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                 ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap", "nvmlClocksThrottleReasonSwPowerCap"))
+        masks = [(nm, getattr(n, a, None) or getattr(n, b, 0)) for nm, a, b in names]
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons", None)
+        while not self._stop:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                bits = int(get_reasons(self.h)) if get_reasons else 0
+                flags = ["Active" if (bits & m) else "Not Active" for _, m in masks]
+                self.rows.append((time.time(), f"{sm}, {self.max_sm}, 0, " + ", ".join(flags)))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(self.PERIOD)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
@@ -97,12 +131,14 @@ class ClockSampler:
         self.t1 = time.time()
 
     def stop(self):
-        if not self.proc:
+        self._stop = True
+        if self.proc:
+            time.sleep(0.05)
+            self.proc.terminate()
+        if not self.proc and not self.nvml:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["unavailable"])
-        time.sleep(0.05)
-        self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        rows = [r for (t, r) in self.rows if self.t0 is None or (self.t0 <= t <= (self.t1 or t) + 0.03)]
+        rows = [r for (t, r) in list(self.rows) if self.t0 is None or (self.t0 <= t <= (self.t1 or t) + 0.03)]
         for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
@@ -115,7 +151,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
+                    reasons=sorted(reasons), samples=len(sm), source="nvml" if self.nvml else "nvidia-smi")
 
 
 def conv_flops(spec, roi, level_dims):

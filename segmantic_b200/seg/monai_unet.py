@@ -195,7 +195,14 @@ def predict_volume(net: Net, image: torch.Tensor, affine: Optional[np.ndarray] =
     if nd == 2:
         lab = lab[0]
     eng.check()
-    return lab if return_device else lab.cpu()
+    if return_device:
+        return lab
+    # device -> host into pinned memory (torch's caching host allocator reuses the block across calls; a pageable
+    # destination costs an allocation plus a staged copy per call)
+    host = torch.empty(lab.shape, dtype=lab.dtype, pin_memory=True)
+    host.copy_(lab, non_blocking=True)
+    torch.cuda.current_stream(dev).synchronize()
+    return host
 
 
 def _nearest_back(lab: torch.Tensor, record) -> torch.Tensor:
