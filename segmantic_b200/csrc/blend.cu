@@ -9,6 +9,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <stdlib.h>
 
 namespace sgm {
 
@@ -276,6 +277,130 @@ __global__ void __launch_bounds__(kGatherWarps * 32) gather_blend_cw_kernel(cons
   }
 }
 
+// Streaming form of the deferred blend (labels, optionally logits): one thread owns FOUR consecutive axis-2 voxels and
+// ALL classes (CT per pass) -- the covering-window address arithmetic is done once per window instead of once per
+// (window, class), the class reduction needs no shared memory or block barrier, and a thread has CT independent
+// 16-byte loads in flight per window (a warp reads CT contiguous 512-byte runs).  ~10 instructions per load instead
+// of ~110 in the warp-per-class kernel above, which stays for VEC = 1 geometries and the softmax output.
+//
+// argmax(acc / count) without dividing every class: x -> fdiv_rn(x, count) is monotonic (count > 0), so the winner is
+// the lowest class whose QUOTIENT equals the quotient of the largest sum.  Scanning classes upwards, a sum that is
+// larger by more than 2^-22 relative certainly has a larger quotient; anything closer (or tiny magnitudes, where the
+// quotient could underflow) is decided by the two exact divisions -- the labels are bit-identical to
+// `torch.argmax(acc / count)` while the common case does no division at all.
+template <int CT, bool FULL>
+__global__ void __launch_bounds__(128, 4) gather_blend_vt_kernel(const GatherArgs a) {
+  __shared__ int s_st[3][SGM_MAX_STARTS];
+  __shared__ float s_im[3][512];
+  for (int i = threadIdx.x; i < 3 * SGM_MAX_STARTS; i += blockDim.x) s_st[i / SGM_MAX_STARTS][i % SGM_MAX_STARTS] = a.starts[i];
+  for (int i = threadIdx.x; i < a.roi[0]; i += blockDim.x) s_im[0][i] = a.imap0[i];
+  for (int i = threadIdx.x; i < a.roi[1]; i += blockDim.x) s_im[1][i] = a.imap1[i];
+  for (int i = threadIdx.x; i < a.roi[2]; i += blockDim.x) s_im[2][i] = a.imap2[i];
+  __syncthreads();
+  const int C = a.channels;
+  const int nq = a.d2 >> 2;  // voxel quads per row
+  const long long vox = (long long)a.nx * a.d1 * a.d2;
+  const long long total = (long long)a.nx * a.d1 * nq;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
+    const int zq = (int)(i % nq);
+    const long long row = i / nq;
+    const int y = (int)(row % a.d1), xl = (int)(row / a.d1);
+    const int x = xl + a.x0, z = zq * 4;
+    int p_lo, p_hi, q_lo, q_hi, r_lo, r_hi;
+    cover_range(s_st[0], a.n_starts[0], a.roi[0], x, p_lo, p_hi);
+    cover_range(s_st[1], a.n_starts[1], a.roi[1], y, q_lo, q_hi);
+    cover_range(s_st[2], a.n_starts[2], a.roi[2], z, r_lo, r_hi);
+    // ---- count map, MONAI's window order and roundings
+    float cnt[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int p = p_lo; p <= p_hi; ++p) {
+      const float g0 = s_im[0][x - s_st[0][p]];
+      for (int q = q_lo; q <= q_hi; ++q) {
+        const float g01 = __fmul_rn(g0, s_im[1][y - s_st[1][q]]);
+        for (int r = r_lo; r <= r_hi; ++r) {
+          const float* g2 = &s_im[2][z - s_st[2][r]];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) cnt[k] = __fadd_rn(cnt[k], fmaxf(__fmul_rn(g01, g2[k]), a.floor));
+        }
+      }
+    }
+    const int pa = max(p_lo, a.a0_begin), pb = min(p_hi, a.a0_end - 1);  // windows of this rank
+    const long long v = ((long long)xl * a.d1 + y) * a.d2 + z;
+    float best[4] = {0.f, 0.f, 0.f, 0.f};   // undivided sum of the current winner
+    float qbest[4] = {0.f, 0.f, 0.f, 0.f};  // logits mode: its quotient
+    int arg[4] = {0, 0, 0, 0};
+    for (int c0 = 0; c0 < C; c0 += CT) {
+      float acc[CT][4];
+#pragma unroll
+      for (int c = 0; c < CT; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f;
+      const float* wl_c = a.wl + (long long)c0 * a.cstride + z;
+      for (int p = pa; p <= pb; ++p) {
+        const long long w0 = (long long)(p - a.a0_begin) * a.n_starts[1];
+        const int off0 = (x - s_st[0][p]) * a.roi[1];
+        for (int q = q_lo; q <= q_hi; ++q) {
+          const float* src01 = wl_c + (w0 + q) * a.n_starts[2] * a.win_stride + (long long)(off0 + (y - s_st[1][q])) * a.roi[2];
+          for (int r = r_lo; r <= r_hi; ++r) {
+            const float* src = src01 + r * a.win_stride - s_st[2][r];
+            float4 t[CT];
+#pragma unroll
+            for (int c = 0; c < CT; ++c)
+              if (FULL || c0 + c < C) t[c] = __ldcs(reinterpret_cast<const float4*>(src + c * a.cstride));
+#pragma unroll
+            for (int c = 0; c < CT; ++c)
+              if (FULL || c0 + c < C) {
+                acc[c][0] = __fadd_rn(acc[c][0], t[c].x), acc[c][1] = __fadd_rn(acc[c][1], t[c].y);
+                acc[c][2] = __fadd_rn(acc[c][2], t[c].z), acc[c][3] = __fadd_rn(acc[c][3], t[c].w);
+              }
+          }
+        }
+      }
+      if (a.logits) {  // normalised logits wanted: divide everything, plain argmax on the quotients
+#pragma unroll
+        for (int c = 0; c < CT; ++c)
+          if (FULL || c0 + c < C) {
+            float qv[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              qv[k] = __fdiv_rn(acc[c][k], cnt[k]);
+              if (c0 + c == 0 || qv[k] > qbest[k]) qbest[k] = qv[k], arg[k] = c0 + c;
+            }
+            __stcs(reinterpret_cast<float4*>(a.logits + (long long)(c0 + c) * vox + v), make_float4(qv[0], qv[1], qv[2], qv[3]));
+          }
+      } else {
+#pragma unroll
+        for (int c = 0; c < CT; ++c)
+          if (FULL || c0 + c < C) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float s = acc[c][k], m = best[k];
+              if (c0 + c == 0) {
+                best[k] = s;
+              } else if (s > m) {
+                const float mag = fmaxf(fabsf(s), fabsf(m));
+                const bool clear = (s - m) > mag * 2.384185791015625e-07f && fminf(fabsf(s), fabsf(m)) > 1e-30f && mag < 1e30f;
+                if (clear || __fdiv_rn(s, cnt[k]) > __fdiv_rn(m, cnt[k])) best[k] = s, arg[k] = c0 + c;
+              }
+            }
+          }
+      }
+    }
+    if (a.labels)
+      *reinterpret_cast<uchar4*>(a.labels + v) = make_uchar4((uint8_t)arg[0], (uint8_t)arg[1], (uint8_t)arg[2], (uint8_t)arg[3]);
+  }
+}
+
+template <int CT>
+int launch_gather_vt(const GatherArgs& a, cudaStream_t st) {
+  const long long total = (long long)a.nx * a.d1 * (a.d2 >> 2);
+  const int blocks = (int)std::max<long long>(1, std::min<long long>((total + 127) / 128, 148LL * 32));
+  if (a.channels % CT == 0)
+    gather_blend_vt_kernel<CT, true><<<blocks, 128, 0, st>>>(a);
+  else
+    gather_blend_vt_kernel<CT, false><<<blocks, 128, 0, st>>>(a);
+  SGM_CUDA_CHECK(cudaGetLastError());
+  return SGM_OK;
+}
+
 }  // namespace
 
 int launch_gather_blend(const float* wl, int channels, const sgm_sw_cfg* cfg, const int* starts_dev,
@@ -296,6 +421,14 @@ int launch_gather_blend(const float* wl, int channels, const sgm_sw_cfg* cfg, co
   if (channels > 64) {
     set_error("deferred blend supports at most 64 classes, got %d", channels);
     return SGM_ERR_UNSUPPORTED;
+  }
+  static const bool force_cw = getenv("SGM_BLEND_CW") != nullptr;  // A/B switch: the warp-per-class kernel
+  if (vec4 && !probs && !force_cw && std::max(a.roi[0], std::max(a.roi[1], a.roi[2])) <= 512) {
+    // classes per pass: a divisor of C keeps the unrolled class loops free of guards (no spills)
+    if (channels <= 4) return launch_gather_vt<4>(a, st);
+    if (channels % 10 == 0) return launch_gather_vt<10>(a, st);
+    if (channels <= 8 || channels % 8 == 0) return launch_gather_vt<8>(a, st);
+    return launch_gather_vt<10>(a, st);
   }
   const int nwarps = std::min(channels, kGatherWarps);
   const long long nrows = (long long)a.nx * a.d1;

@@ -627,6 +627,7 @@ void tc_free(TcConv* c) {
   free_plans(c->plan_cache);
   ps_free(c);
   pst_free(c);
+  rs_free(c);
   if (c->w) cudaFree(c->w);
   if (c->bias) cudaFree(c->bias);
   delete c;
@@ -878,6 +879,7 @@ int tc_pack(const sgm_conv_desc* m, const sgm_conv_desc* second, int spatial_dim
   if (!second) {
     int rc = ps_pack(*m, c);
     if (!rc) rc = pst_pack(*m, c);
+    if (!rc) rc = rs_pack(*m, c);
     if (rc) {
       tc_free(c);
       return rc;
@@ -1135,6 +1137,7 @@ static void free_plans(void* p) { delete reinterpret_cast<std::vector<PlanEntry>
 int tc_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t st) {
   SGM_REQUIRE(io.cg0 + io.cg1 == c.cgin, SGM_ERR_INVALID, "tc_launch: input channel groups %d+%d != %d", io.cg0,
               io.cg1, c.cgin);
+  if (rs_applicable(c, io)) return rs_launch(c, io, error_flag_dev, st);
   if (ps_applicable(c, io)) return ps_launch(c, io, error_flag_dev, st);
   if (pst_applicable(c, io)) return pst_launch(c, io, error_flag_dev, st);
   const int key[8] = {io.id[0], io.id[1], io.id[2], io.od[0], io.od[1], io.od[2], io.n, io.cg0};

@@ -55,6 +55,11 @@ struct TcConv {
   __nv_bfloat16* pst_w = nullptr;  // device [8*ncgp][2][128][8], row n' = class*16 + co
   int pst_ncgp = 0;                // input channel pairs of groups (2 or 4); 0 = not eligible
   void* pst_plan_cache = nullptr;
+  // row-sweep packing (conv_rs.cu): the head (<= 16 -> <= 10 channels, planar fp32 output) folds the d0 AND d1 taps
+  // into the MMA N dimension through overlapping accumulator columns
+  __nv_bfloat16* rs_w = nullptr;   // device [3 rotations][3 k2][2][9*CP+16][8]
+  int rs_cp = 0;                   // accumulator columns per (output row, plane slot); 0 = not eligible
+  void* rs_plan_cache = nullptr;
 };
 
 struct TcIO {
@@ -96,6 +101,12 @@ int ps_pack(const sgm_conv_desc& d, TcConv* c);          // fills ps_* when the 
 bool ps_applicable(const TcConv& c, const TcIO& io);
 int ps_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t st);
 void ps_free(TcConv* c);
+
+// row-sweep family (conv_rs.cu)
+int rs_pack(const sgm_conv_desc& d, TcConv* c);
+bool rs_applicable(const TcConv& c, const TcIO& io);
+int rs_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t st);
+void rs_free(TcConv* c);
 
 // transposed plane-sweep family (conv_pst.cu)
 int pst_pack(const sgm_conv_desc& d, TcConv* c);

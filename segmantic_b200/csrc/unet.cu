@@ -883,7 +883,9 @@ extern "C" int32_t sgm_unet_check(sgm_unet* net, void* stream) {
   SGM_CUDA_CHECK(cudaMemcpy(&flag, net->err_dev, sizeof(int), cudaMemcpyDeviceToHost));
   if (flag) {
     cudaMemset(net->err_dev, 0, sizeof(int));
-    set_error("tcgen05 conv pipeline timed out (wait code %d: 1 weight ring, 2 TMEM drain, 3 weights, 4 accumulator)", flag);
+    set_error("tcgen05 conv pipeline timed out (wait code %d: 1 weight ring, 2 TMEM drain, 3 weights, 4 accumulator; 2x plane "
+              "sweep; row sweep: 41 ring slot, 42 weights, 43 plane landed, 44 row cleared, 45 residual plane, 46 row multiplied)",
+              flag);
     return SGM_ERR_CUDA;
   }
   return SGM_OK;
