@@ -41,6 +41,9 @@ CLASSES = 10
 OVERLAP = 0.5
 MODE = "gaussian"
 METRIC = "3D UNet sliding-window predict throughput"
+# ncu --set full captures of this round (profiles/r01c_ncu_top_kernels.md): dram__bytes_read.sum + dram__bytes_write.sum
+NCU_HEAD_TRAFFIC = 3.543512e9 + 4.367288e9   # rs_conv_kernel<10,10>, one 125-window launch
+NCU_BLEND_TRAFFIC = 4.545447e9 + 8.923e6     # gather_blend_vt_kernel<10>, the 256^3 blend
 UNIT = "Mvoxel/s"
 
 
@@ -403,17 +406,23 @@ def run_b200(args):
         barrier()
         t0 = time.perf_counter()
         e2e_steps = max(1, args.steps)
+        e2e_calls = []
         for _ in range(e2e_steps):
+            tc0 = time.perf_counter()
             lab = predict_volume(pnet, host, None, (), **kw)  # returns a HOST uint8 label map
+            e2e_calls.append((time.perf_counter() - tc0) * 1e3)
         torch.cuda.synchronize(dev)
         e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+        log(f"[rank {rank}] e2e per-call ms: {[round(c, 2) for c in e2e_calls]}; launches per call "
+            f"{pnet.engine(args.precision).last_launch_count}")
         t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
         e2e = dict(value=float(np.prod(VOL)) * world / (e2e_ms * 1e-3) / 1e6, unit=UNIT,
                    h2d_bytes_per_step=int(host.numel() * 4), d2h_bytes_per_step=int(lab.numel()),
-                   ms_per_step=e2e_ms,
+                   ms_per_step=e2e_ms, ms_per_call=dict(min=min(e2e_calls), median=float(np.median(e2e_calls)),
+                                                        max=max(e2e_calls)),
                    note="predict_volume(host fp32 volume) -> host uint8 labels; N>1: one 256^3 volume per rank")
 
     if rank != 0:
@@ -452,13 +461,18 @@ def run_b200(args):
         head_bytes = (esz * CLASSES + 4 * CLASSES) * roi_vox   # read C bf16 channels, write C fp32 weighted logits
         gbs = head_bytes * wins_per_launch / t_launch / 1e9
         tfs = head_flop * wins_per_launch / t_launch / 1e12
-        # ncu --set full (profiles/r01b_ncu_top_kernels.md): dram__bytes_read + write of one 32-window launch
-        traffic = 925.79e6 + 1084.31e6 if (CLASSES == 10 and args.precision == "bf16" and args.sw_batch == 32) else None
-        roofline = dict(kernel="ps_conv_kernel<10,1,PLANAR>[head: conv CxC k3 (d0 taps folded into MMA N) + identity "
-                               "residual + importance-weighted fp32 logits]",
+        # ncu --set full (profiles/r01c_ncu_top_kernels.md): dram__bytes_read + write of one 125-window launch
+        row_sweep = not os.environ.get("SGM_NO_RS")
+        traffic = NCU_HEAD_TRAFFIC if (CLASSES == 10 and args.precision == "bf16" and wins_per_launch == 125
+                                       and row_sweep) else None
+        roofline = dict(kernel=("rs_conv_kernel<10,10>[head: conv CxC k3, d0 and d1 taps folded into MMA N through "
+                                "overlapping accumulator columns + identity residual + importance-weighted fp32 logits]"
+                                if row_sweep else
+                                "ps_conv_kernel<10,1,PLANAR>[head: conv CxC k3 (d0 taps folded into MMA N) + identity "
+                                "residual + importance-weighted fp32 logits]"),
                         bound="hbm", achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=gbs / pk["hbm"],
-                        traffic=traffic, traffic_note="ncu dram bytes of a 32-window launch (algorithmic: 1.70 GB + "
-                                                      "16-channel padding of the bf16 input = 2.04 GB)",
+                        traffic=traffic, traffic_note="ncu dram bytes of a 125-window launch (algorithmic: 6.64 GB + "
+                                                      "16-channel padding of the bf16 input = 7.96 GB)",
                         peak_source=pk["source"], us_per_window=per_window_s * 1e6, us_per_launch=t_launch * 1e6,
                         windows_per_launch=wins_per_launch, algorithmic_bytes_per_window=head_bytes,
                         algorithmic_bytes_per_launch=head_bytes * wins_per_launch,
@@ -478,10 +492,11 @@ def run_b200(args):
         blend_bytes = 4.0 * CLASSES * n_win * roi_vox + float(np.prod(VOL))
         if blend_prof[2] > 0 and blend_prof[1] > 0:
             t = blend_prof[1] * 1e-3 / blend_prof[2]
-            blend_roof = dict(kernel="gather_blend_cw_kernel[sum covering windows + count + normalise + argmax]",
+            blend_roof = dict(kernel="gather_blend_vt_kernel<10>[sum covering windows in MONAI order + count + "
+                                     "division-free exact argmax]",
                               bound="hbm", achieved=blend_bytes / t / 1e9, peak=pk["hbm"], unit="GB/s",
                               frac=blend_bytes / t / 1e9 / pk["hbm"],
-                              traffic=(4423.76e6 + 12.22e6) if CLASSES == 10 else None, peak_source=pk["source"],
+                              traffic=NCU_BLEND_TRAFFIC if CLASSES == 10 else None, peak_source=pk["source"],
                               ms_per_launch=t * 1e3, algorithmic_bytes_per_launch=blend_bytes,
                               formula="4*C*n_windows*roi^3 (weighted logits read once) + 1*V (labels written)")
 
@@ -499,7 +514,8 @@ def run_b200(args):
                 config=dict(workload="configs[1]: MONAI UNet3D (16-32-64-128-256, strides 2, 1 ch, 10 tissues), "
                                      f"synthetic {gshape[0]}x{gshape[1]}x{gshape[2]} volume, roi 96^3, overlap 0.5, "
                                      "gaussian blend, argmax labels",
-                            windows=int(n_win if world == 1 else sched.n_windows), sw_batch=args.sw_batch,
+                            windows=int(n_win if world == 1 else sched.n_windows),
+                            sw_batch=max(args.sw_batch, int(os.environ.get("SGM_SW_BATCH", engine.DEVICE_SW_BATCH))),
                             parallelism=(f"owned-windows{world}+p2p-halo" if owned else f"slab{world}") if world > 1 else "single",
                             l2="no flush: per-step working set (67 MB volume + 671 MB accumulator + activations) "
                                "exceeds the 126 MB L2"),
@@ -522,7 +538,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--sw-batch", type=int, default=32)
+    ap.add_argument("--sw-batch", type=int, default=32,
+                    help="MONAI's sw_batch_size argument; the device batches max(this, engine.DEVICE_SW_BATCH) windows")
     ap.add_argument("--cpu-windows", type=int, default=32, help="windows in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-profile", action="store_true")

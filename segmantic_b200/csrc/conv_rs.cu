@@ -44,7 +44,8 @@ namespace {
 using namespace tcptx;
 
 constexpr int kRsEpiWarps = 16;
-constexpr int kRsThreads = (kRsEpiWarps + 2) * 32;  // + producer warp + issuer warp
+constexpr int kRsIssuers = 2;                        // MMA issuer warps (alternating input rows)
+constexpr int kRsThreads = (kRsEpiWarps + 1 + kRsIssuers) * 32;  // + producer warp + issuer warps
 constexpr int kRsSmemMax = 227 * 1024;
 constexpr int kRsRingMax = 6;
 constexpr int kRsRowsMax = 16;                       // output rows per strip (TMEM: t1 * RP <= 512 columns)
@@ -57,7 +58,7 @@ struct RsArgs {
   int nstrips, nunits;
   int R;               // plane ring depth
   int nq;              // TMEM lane quarters that hold real positions: ceil(D2 / 32)
-  int RC, rc_log2;     // input rows per tcgen05.commit ("chunk multiplied" barrier), a power of two
+  int issuers;         // MMA issuer warps in use: 1 (deterministic accumulation order, default) or 2 (SGM_RS_ISSUERS=2)
   int c_real;
   int res_mode;        // 0 none, 2 identity (centre of the input plane, read from the ring)
   int pl_weighted;
@@ -71,7 +72,7 @@ struct RsArgs {
   float imap_floor;
   int* error_flag;
   long long* trace;    // SGM_TRACE: clock stamps / wait cycles of CTA 0
-  int abl;             // SGM_RS_ABL: timing ablations (wrong results): 1 no stores, 2 no residual, 4 no clear, 8 narrow MMAs, 16 no TMEM loads
+  int abl;             // SGM_RS_ABL: timing ablations of the issuer (wrong results): 8 narrow MMAs, 256 no MMAs, 1 one MMA per row
 };
 
 template <int NC>
@@ -133,8 +134,8 @@ __host__ __device__ constexpr int rs_rp(int cp) { return rs_pad16(3 * cp); }    
 __host__ __device__ constexpr int rs_nb(int cp) { return 3 * rs_rp(cp); }                    // B rows per K chunk: three k1 blocks of RP rows
 __host__ __device__ constexpr int rs_w_bytes(int cp) { return 3 * 3 * 2 * rs_nb(cp) * 16; }  // [rot][k2][kchunk][NB][8 bf16]
 
-// CP = accumulator columns per (output row, plane slot) >= real output channels
-template <int CP>
+// CP = accumulator columns per (output row, plane slot) >= CR = real output channels (stores unrolled without guards)
+template <int CP, int CR>
 __global__ void __launch_bounds__(kRsThreads, 1) rs_conv_kernel(const RsArgs a, const __grid_constant__ CUtensorMap tmap) {
   constexpr int RP = rs_rp(CP);  // columns per output row; the RP - 3*CP padding columns only ever receive +0.0
   constexpr int N3 = RP, N6 = 2 * RP, N9 = 3 * RP;
@@ -156,12 +157,12 @@ __global__ void __launch_bounds__(kRsThreads, 1) rs_conv_kernel(const RsArgs a, 
   auto PFULL = [&](int s) { return bar0 + 8u * (1 + s); };
   auto PEMPTY = [&](int s) { return bar0 + 8u * (1 + kRsRingMax + s); };
   auto FULL = [&](int c) { return bar0 + 8u * (1 + 2 * kRsRingMax + c); };                      // input rows of chunk c multiplied
-  auto CLR = [&](int o) { return bar0 + 8u * (1 + 2 * kRsRingMax + (kRsRowsMax + 2) + o); };    // output row o cleared
+  auto CLR = [&](int c) { return bar0 + 8u * (1 + 2 * kRsRingMax + (kRsRowsMax + 2) + c); };    // output rows 4c .. 4c+3 cleared
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 2 * kRsRingMax + (kRsRowsMax + 2) + kRsRowsMax);
   volatile int* abort_s = reinterpret_cast<volatile int*>(tmem_slot + 1);
   const int D0 = a.D[0], t1 = a.t1, H1 = a.H1, R = a.R, nq = a.nq;
   const bool tr = a.trace != nullptr && blockIdx.x == 0;
-  constexpr int PW = kRsEpiWarps, IW = kRsEpiWarps + 1;
+  constexpr int PW = kRsEpiWarps, IW = kRsEpiWarps + 1;  // producer warp, first issuer warp
 
   if (tid == 0) {
     *abort_s = 0;
@@ -169,10 +170,10 @@ __global__ void __launch_bounds__(kRsThreads, 1) rs_conv_kernel(const RsArgs a, 
     const uint32_t readers = a.res_mode == 2 ? (uint32_t)(4 * nq) : 0u;
     for (int s = 0; s < kRsRingMax; ++s) {
       mbar_init(PFULL(s), 1);
-      mbar_init(PEMPTY(s), 1 + readers);  // MMA commit + the epilogue warps that read the identity residual
+      mbar_init(PEMPTY(s), (uint32_t)a.issuers + readers);  // MMA commits + the epilogue warps that read the identity residual
     }
-    for (int i = 0; i < kRsRowsMax + 2; ++i) mbar_init(FULL(i), 1);
-    for (int o = 0; o < kRsRowsMax; ++o) mbar_init(CLR(o), (uint32_t)nq);
+    for (int i = 0; i < kRsRowsMax + 2; ++i) mbar_init(FULL(i), (uint32_t)a.issuers);
+    for (int c = 0; c < kRsRowsMax / 4; ++c) mbar_init(CLR(c), (uint32_t)(nq * max(min(4, t1 - 4 * c), 1)));  // every row of the chunk, every lane quarter
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (tr) a.trace[0] = clock64();
   }
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(kRsThreads, 1) rs_conv_kernel(const RsArgs a, 
   }
   // zero the ring once: slack behind the rows (read by the 128-row tiles, results discarded) stays finite
   for (uint32_t i = tid; i < a_bytes / 16; i += kRsThreads) reinterpret_cast<uint4*>(ring)[i] = make_uint4(0, 0, 0, 0);
-  if (tid < 32) bias_s[tid] = tid < a.c_real ? __ldg(a.bias + tid) : 0.f;
+  if (tid < 32) bias_s[tid] = tid < CR ? __ldg(a.bias + tid) : 0.f;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tc_fence_before();
   __syncthreads();
@@ -210,14 +211,14 @@ __global__ void __launch_bounds__(kRsThreads, 1) rs_conv_kernel(const RsArgs a, 
       bulk_g2s(smem_u32(w_smem), a.w, W_BYTES, WBAR);
       const uint32_t ring_base = smem_u32(ring);
       const uint32_t tx = 2u * (uint32_t)(H1 * a.W) * 16u;
-      int G = 0;  // input planes loaded so far
+      int slot = 0;
+      uint32_t ephase = 1;  // parity that reads "never used" on a fresh barrier
       bool ok = true;
       for (int kl = 0; kl < my_units && ok; ++kl) {
         const int unit = (int)blockIdx.x + kl * (int)gridDim.x;
         const int n = unit / a.nstrips, strip = unit - n * a.nstrips;
-        for (int x0 = 0; x0 < D0; ++x0, ++G) {
-          const int slot = G % R;
-          if (G >= R) ok = rs_wait(PEMPTY(slot), (uint32_t)(G / R - 1) & 1u, a.error_flag, 41, abort_s);
+        for (int x0 = 0; x0 < D0; ++x0) {
+          ok = rs_wait(PEMPTY(slot), ephase, a.error_flag, 41, abort_s);
           if (!ok) break;
           mbar_expect_tx(PFULL(slot), tx);
           // one 5-D box {8 ch, W positions, H1 rows, 1 plane, 1 group}; coordinates outside the window are zero-filled
@@ -226,14 +227,27 @@ __global__ void __launch_bounds__(kRsThreads, 1) rs_conv_kernel(const RsArgs a, 
           for (int cg = 0; cg < 2; ++cg)
             tma_load_5d(ring_base + (uint32_t)slot * plane_bytes + (uint32_t)(cg * a.GS) * 16u, &tmap, 0, -1,
                         strip * t1 - 1, x0, n * 2 + cg, PFULL(slot));
+          if (++slot == R) slot = 0, ephase ^= 1u;
         }
       }
     }
-  } else if (warp == IW) {
-    // ============================ MMA issuer: one elected lane ============================
+  } else if (warp >= IW && warp < IW + a.issuers) {
+    // ============================ MMA issuer(s): one elected lane per warp ============================
+    // Default: ONE issuer -- every output row then receives its 27 x (channel pair) partial products in a fixed order
+    // (planes, rows, d2 taps ascending) that does not depend on the strip height, the batch or the timing, so logits
+    // are reproducible bit for bit between runs, batch sizes and the multi-GPU partitions.  SGM_RS_ISSUERS=2 shares
+    // the rows between two warps (alternating rows): faster issue, but the two instruction streams interleave in the
+    // tensor pipe in a timing-dependent order, i.e. the fp32 summation order is no longer fixed.
+    // This loop runs on ONE thread next to a tensor pipe that wants a new MMA every ~56 clk, at ~6 clk per dependent
+    // instruction: no divisions (the first version spent 500-700 clk per row on `%` and `/`), ring / rotation / parity
+    // state carried incrementally, operand descriptors advanced by additions -- and the rows are shared by two issuer
+    // warps.  Accumulation commutes and the tensor pipe executes whole MMAs one after another, so the interleaving of
+    // the two instruction streams does not matter; each issuer commits its own MMAs ("multiplied" barriers count two).
     if (elect_one()) {
+      const int iw = warp - IW, ni = a.issuers;
       auto idesc = [](uint32_t n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24); };
-      const uint32_t id3 = idesc(a.abl & 8 ? N3 : N3), id6 = idesc(a.abl & 8 ? N3 : N6), id9 = idesc(a.abl & 8 ? N3 : N9);
+      const uint32_t id3 = idesc(N3), id6 = idesc(a.abl & 8 ? N3 : N6), id9 = idesc(a.abl & 8 ? N3 : N9);
+      const bool no_mma = a.abl & 256, one_mma = a.abl & 1;
       const uint32_t ring16 = smem_u32(ring) >> 4;
       const uint32_t w16 = smem_u32(w_smem) >> 4;
       const uint64_t d_hi = (uint64_t)(8u | (1u << 14)) << 32;  // SBO = 128 B: 8 consecutive positions / B rows
@@ -241,19 +255,14 @@ __global__ void __launch_bounds__(kRsThreads, 1) rs_conv_kernel(const RsArgs a, 
       const uint32_t b_lbo = ((uint32_t)NB & 0x3FFFu) << 16;
       const uint32_t plane16 = 2u * (uint32_t)a.GS;
       const uint32_t W = (uint32_t)a.W;
-      const int RC = a.RC;
-      const bool no_clr = a.abl & 64, no_mma = a.abl & 256;
       bool ok = rs_wait(WBAR, 0u, a.error_flag, 42, abort_s);
       long long wait_p = 0, wait_c = 0;
-      if (tr) a.trace[1] = clock64();
-      // The loop below runs on ONE thread next to a tensor pipe that needs a new MMA every ~56 clk: no divisions (an
-      // integer division is ~150 clk of dependent instructions -- the first version spent 500-700 clk per row on
-      // `%` and `/`), all ring / rotation / parity state is carried incrementally.
+      if (tr && iw == 0) a.trace[1] = clock64();
       int slot = 0;          // ring entry of the next real input plane
       uint32_t pphase = 0;   // parity of its "landed" barrier
       uint32_t rot = 0;      // virtual output plane index of (xi - 1), mod 3: which weight rotation
-      uint32_t vpar = 1;     // parity of Vc = V0 - 1 (V0 = virtual plane counter of the CTA)
-      bool first = true;     // V0 == 0: nothing to observe yet
+      uint32_t vpar = 1;     // parity of the "cleared" phase to observe (virtual plane counter of the CTA - 1)
+      bool first = true;     // nothing to observe before the very first plane
       for (int kl = 0; kl < my_units && ok; ++kl) {
         // virtual input planes 0 .. D0+1: the last two carry no MMAs, they only keep the barrier phases in step
         for (int xi = 0; xi < D0 + 2 && ok; ++xi) {
@@ -264,39 +273,80 @@ __global__ void __launch_bounds__(kRsThreads, 1) rs_conv_kernel(const RsArgs a, 
             ok = rs_wait(PFULL(slot), pphase, a.error_flag, 43, abort_s);
             if (tr) wait_p += clock64() - tw0;
             if (!ok) break;
+            tc_fence_after();
           }
-          const bool wait_clr = !first && !no_clr;
           const uint32_t wrot = (w16 + rot * WROT16) | b_lbo;
-          const uint32_t aplane = (ring16 + (uint32_t)slot * plane16) | a_lbo;
-          int cc = 0, ci = 0;  // rows since the last commit, chunk index
-          // input row r = i - 1 feeds output rows r-1 (k1 = 2), r (k1 = 1), r+1 (k1 = 0) = B rows [0,RP) [RP,2RP) [2RP,3RP)
-          auto row = [&](int i, uint32_t boff, uint32_t id, uint32_t col) {
-            if (wait_clr && i < t1) {  // output rows i-2 and i-1 were observed with the previous input rows
-              long long tw0 = 0;
-              if (tr) tw0 = clock64();
-              ok = rs_wait(CLR(i), vpar, a.error_flag, 44, abort_s);
-              if (tr) wait_c += clock64() - tw0;
-            }
-            if (ok && real && !no_mma) {
+          uint32_t arow = ((ring16 + (uint32_t)slot * plane16) | a_lbo) + (uint32_t)iw * W;  // A descriptor of this issuer's next row
+          const uint32_t astep = (uint32_t)ni * W;
+          // Barrier operations cost 100-300 clk of this thread's time each (measured: a loop of nothing but two polls per
+          // row ran at 400 clk / row), so both directions work on chunks of four rows: one "cleared" poll when the issuer
+          // enters a chunk of output rows, one commit ("multiplied") when it leaves a chunk of input rows.
+          // Input row r = i - 1 feeds output rows r-1 (k1 = 2), r (k1 = 1), r+1 (k1 = 0) = B rows [0,RP) [RP,2RP) [2RP,3RP);
+          // the first / last two rows of the strip use the trailing / leading part of the same B tile.
+          if (ni == 1) {
+            // Single issuer, straight-line form: head rows (-1, 0), uniform middle rows, tail rows (t1-1, t1); the
+            // only per-row work besides the three MMAs is two additions and two chunk tests.
+#define SGM_RS_MMA3(AROW, B0, ID, COL)                                                       \
+  do {                                                                                       \
+    tc_mma(tmem_base + (COL), d_hi | (AROW), d_hi | (B0), (ID), 1u);                         \
+    tc_mma(tmem_base + (COL), d_hi | ((AROW) + 1u), d_hi | ((B0) + 2u * NB), (ID), 1u);      \
+    tc_mma(tmem_base + (COL), d_hi | ((AROW) + 2u), d_hi | ((B0) + 4u * NB), (ID), 1u);      \
+  } while (0)
+            if (!first) {
+              if (!rs_wait(CLR(0), vpar, a.error_flag, 44, abort_s)) { ok = false; break; }
               tc_fence_after();
-              const uint32_t abase = aplane + (uint32_t)i * W;
-#pragma unroll
-              for (int k2 = 0; k2 < 3; ++k2)
-                tc_mma(tmem_base + col, d_hi | (abase + (uint32_t)k2), d_hi | (wrot + (uint32_t)(k2 * 2 * NB) + boff), id, 1u);
             }
-            // tcgen05.commit costs ~400 clk of issue time: one "chunk multiplied" barrier per RC rows
-            if (++cc == RC || i + 1 == H1) {
-              if (ok) tc_commit(FULL(ci));
-              ++ci, cc = 0;
+            if (real) {
+              SGM_RS_MMA3(arow, wrot + 2u * RP, id3, 0u);
+              SGM_RS_MMA3(arow + W, wrot + (uint32_t)RP, id6, 0u);
             }
-          };
-          row(0, 2 * RP, id3, 0);
-          if (ok) row(1, RP, id6, 0);
-          for (int i = 2; i < t1 && ok; ++i) row(i, 0, id9, (uint32_t)(i - 2) * RP);
-          if (ok) row(t1, 0, id6, (uint32_t)(t1 - 2) * RP);
-          if (ok) row(t1 + 1, 0, id3, (uint32_t)(t1 - 1) * RP);
+            arow += 2u * W;
+            uint32_t col = 0;
+            for (int i = 2; i < t1; ++i, arow += W, col += RP) {
+              if ((i & 3) == 0 && !first) {  // entering the chunk of output rows i .. i+3
+                if (!rs_wait(CLR(i >> 2), vpar, a.error_flag, 44, abort_s)) { ok = false; break; }
+                tc_fence_after();
+              }
+              if (real) SGM_RS_MMA3(arow, wrot, id9, col);
+              if ((i & 3) == 3) tc_commit(FULL(i >> 2));
+            }
+            if (!ok) break;
+            if (real) SGM_RS_MMA3(arow, wrot, id6, col);
+            if ((t1 & 3) == 3) tc_commit(FULL(t1 >> 2));
+            if (real) SGM_RS_MMA3(arow + W, wrot, id3, col + RP);
+            tc_commit(FULL((t1 + 1) >> 2));
+#undef SGM_RS_MMA3
+          } else {
+            int next_commit = 0;
+            for (int i = iw; i < H1 && ok; i += ni, arow += astep) {
+              const int c = i >> 2;
+              if (!first && (i & 3) == iw && 4 * c < t1) {  // entering a chunk: output rows 4c .. 4c+3 (i-2, i-1: previous chunk)
+                long long tw0 = 0;
+                if (tr) tw0 = clock64();
+                ok = rs_wait(CLR(c), vpar, a.error_flag, 44, abort_s);
+                if (tr) wait_c += clock64() - tw0;
+                tc_fence_after();
+              }
+              if (ok && real && !no_mma) {
+                const int r = i - 1;
+                const uint32_t col = (uint32_t)max(r - 1, 0) * RP;
+                const uint32_t b0 = wrot + (r < 0 ? 2u * RP : (r == 0 ? (uint32_t)RP : 0u));
+                const uint32_t id = (r < 0 || r == t1) ? id3 : ((r == 0 || r == t1 - 1) ? id6 : id9);
+                tc_mma(tmem_base + col, d_hi | arow, d_hi | b0, id, 1u);
+                if (!one_mma) {
+                  tc_mma(tmem_base + col, d_hi | (arow + 1u), d_hi | (b0 + 2u * NB), id, 1u);
+                  tc_mma(tmem_base + col, d_hi | (arow + 2u), d_hi | (b0 + 4u * NB), id, 1u);
+                }
+              }
+              if (ok && ((i & 3) == 4 - ni + iw || i + ni >= H1)) {  // this issuer's last row of the chunk
+                tc_commit(FULL(c));
+                next_commit = c + 1;
+              }
+            }
+            for (int c = next_commit; c <= (H1 - 1) >> 2 && ok; ++c) tc_commit(FULL(c));  // chunks without a row of this issuer
+          }
           if (real && ok) {
-            tc_commit(PEMPTY(slot));  // the MMAs that read the plane have completed when this arrives
+            tc_commit(PEMPTY(slot));  // this issuer's MMAs that read the plane have completed when this arrives
             if (++slot == R) slot = 0, pphase ^= 1u;
           }
           first = false;
@@ -304,113 +354,134 @@ __global__ void __launch_bounds__(kRsThreads, 1) rs_conv_kernel(const RsArgs a, 
           if (++rot == 3) rot = 0;
         }
       }
-      if (tr) a.trace[2] = clock64(), a.trace[3] = wait_p, a.trace[4] = wait_c;
+      if (tr && iw == 0) a.trace[2] = clock64(), a.trace[3] = wait_p, a.trace[4] = wait_c;
     }
     __syncwarp();
-  } else if ((warp & 3) < nq) {
+  } else if (warp < kRsEpiWarps && (warp & 3) < nq) {
     // ============================ epilogue warps: group = warp / 4 owns output rows o = group, group + 4, ... ============================
     const int egroup = warp >> 2, quarter = warp & 3;
     const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const int d2 = quarter * 32 + lane;
     const bool valid2 = d2 < a.D[2];
     const bool weighted = a.pl_weighted != 0;
-    const int c_real = a.c_real, res_mode = a.res_mode;
+    const bool res = a.res_mode == 2;
     const long long plane_vox = (long long)a.D[1] * a.D[2];
+    const long long cs = a.pl_cstride;
     const float w2 = (weighted && valid2) ? __ldg(a.imap2 + d2) : 1.f;
-    float bias_r[CP];
+    const float floor_w = weighted ? a.imap_floor : 1.f;
+    float bias_r[CR];
 #pragma unroll
-    for (int c = 0; c < CP; ++c) bias_r[c] = bias_s[c];
-    bool ok = true;
-    const unsigned sleep_ns = 32u;
-    // One lane polls, the warp follows through the shuffle (a warp-wide mbarrier.try_wait is 32 shared-memory
-    // operations on one word: with 12 warps polling, the barrier words became the hot spot of the whole CTA).
-    const bool all_poll = a.abl & 512;
+    for (int c = 0; c < CR; ++c) bias_r[c] = bias_s[c];
+    // One lane polls, the warp follows through the shuffle; a short sleep between polls leaves the issue slots of the
+    // scheduler to the issuer warps.
     auto warp_wait = [&](uint32_t bar, uint32_t parity, int code) {
       bool r = true;
-      if (all_poll) return (bool)__all_sync(0xffffffffu, rs_wait(bar, parity, a.error_flag, code, abort_s, sleep_ns));
-      if (lane == 0) r = rs_wait(bar, parity, a.error_flag, code, abort_s, sleep_ns);
+      if (lane == 0) r = rs_wait(bar, parity, a.error_flag, code, abort_s, 32u);
       return (bool)__shfl_sync(0xffffffffu, (int)r, 0);
     };
+    bool ok = true;
     int rslot = 0;
-    uint32_t rphase = 0;
+    uint32_t rphase = 0, fpar = 0, slot3 = 0;  // parity of the virtual plane counter, and the counter mod 3
     long long wait_f = 0;
     const long long te0 = tr ? clock64() : 0;
     for (int kl = 0; kl < my_units && ok; ++kl) {
       const int unit = (int)blockIdx.x + kl * (int)gridDim.x;
       const int n = unit / a.nstrips, strip = unit - n * a.nstrips;
       const int r0 = strip * t1;
-      float* out_n = a.pl_out + (long long)n * a.pl_nstride + d2;
+      float* out_n = a.pl_out + (long long)n * a.pl_nstride + (long long)r0 * a.D[2] + d2;
+      const uint8_t* res_lane = ring + (size_t)(a.W + d2 + 1) * 16;  // residual of output row 0: input row 1, position d2 + 1
       for (int v = -1; v <= D0 && ok; ++v) {
-        const int V = kl * (D0 + 2) + v + 1;
-        const uint32_t pcol = (uint32_t)(V % 3) * CP;
-        // the output plane is complete once (virtual) input plane v+1 has been multiplied: FULL phase index == V
-        const uint32_t fpar = (uint32_t)V & 1u;
+        // virtual output plane v (counter V = kl * (D0 + 2) + v + 1): slot V % 3, complete once virtual input plane
+        // v + 1 has been multiplied ("multiplied" phase index == V)
+        const uint32_t pcol = slot3 * CP;
         const bool real = v >= 0 && v < D0;
-        if (real && res_mode == 2) {
+        if (real && res) {
           // generic-proxy reads of TMA-written data: observe the plane's own barrier (it completed long ago)
           ok = warp_wait(PFULL(rslot), rphase, 45);
           if (!ok) break;
         }
-        const float g0 = (real && weighted) ? __ldg(a.imap0 + v) : 1.f;
-        for (int o = egroup; o < t1; o += 4) {
+        float g0 = 1.f;
+        if (real && weighted) g0 = __ldg(a.imap0 + v);
+        float* out_v = out_n + (long long)v * plane_vox;
+        const uint8_t* res_v = res_lane + (size_t)rslot * plane_bytes;
+        // A step is a chain of dependent long-latency operations (barrier poll, TMEM load, TMEM store, shared and
+        // global loads: ~1000 clk measured, whatever the amount of arithmetic), so each step handles TWO adjacent output
+        // rows: group g owns rows 2g, 2g+1, then 2g+8, 2g+9.
+        for (int oa = 2 * egroup; oa < t1; oa += 8) {
+          const bool has_b = oa + 1 < t1;
           // input rows o, o+1, o+2 feed output row o: complete when the chunk of input row o+2 has been committed
           long long tw0 = 0;
           if (tr) tw0 = clock64();
-          if (!(a.abl & 128)) ok = warp_wait(FULL((o + 2) >> a.rc_log2), fpar, 46);
+          ok = warp_wait(FULL((oa + (has_b ? 3 : 2)) >> 2), fpar, 46);
           if (tr) wait_f += clock64() - tw0;
           if (!ok) break;
           tc_fence_after();
-          const uint32_t taddr = tlane + (uint32_t)(o * RP) + pcol;
-          uint32_t acc[CP];
-          if (!(a.abl & 16)) {
-            rs_ld<CP>(taddr, acc);
-            tc_ld_wait();
-          } else {
-#pragma unroll
-            for (int c = 0; c < CP; ++c) acc[c] = 0u;
-          }
-          if (!(a.abl & 4)) {
-            rs_st_zero<CP>(taddr);  // the plane three steps later accumulates into these columns again
-            rs_st_wait();
-          }
+          const uint32_t taddr = tlane + (uint32_t)(oa * RP) + pcol;
+          uint32_t acc[2][CP];
+          rs_ld<CP>(taddr, acc[0]);
+          if (has_b) rs_ld<CP>(taddr + RP, acc[1]);
+          tc_ld_wait();
+          rs_st_zero<CP>(taddr);  // the plane three steps later accumulates into these columns again
+          if (has_b) rs_st_zero<CP>(taddr + RP);
+          rs_st_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0 && !(a.abl & 64)) mbar_arrive(CLR(o));
-          const int r1 = r0 + o;
-          if (real && valid2 && r1 < a.D[1]) {
-            float val[CP];
-#pragma unroll
-            for (int c = 0; c < CP; ++c) val[c] = __uint_as_float(acc[c]) + bias_r[c];
-            if (res_mode == 2 && !(a.abl & 2)) {
-              const uint8_t* pl = ring + (size_t)rslot * plane_bytes + (size_t)((o + 1) * a.W + d2 + 1) * 16;
-#pragma unroll
-              for (int pc = 0; pc < (CP + 7) / 8; ++pc) {
-                float rr[8];
-                unpack8(*reinterpret_cast<const uint4*>(pl + (size_t)pc * a.GS * 16), rr);
-#pragma unroll
-                for (int c = 0; c < 8; ++c)
-                  if (8 * pc + c < CP) val[8 * pc + c] += rr[c];
-              }
+          if (lane == 0) {
+            mbar_arrive(CLR(oa >> 2));
+            if (has_b) mbar_arrive(CLR(oa >> 2));  // oa is even: both rows are in the same chunk
+          }
+          if (real && valid2) {
+            float g1[2] = {1.f, 1.f};
+            if (weighted) {
+              g1[0] = __ldg(a.imap1 + min(r0 + oa, a.D[1] - 1));
+              g1[1] = __ldg(a.imap1 + min(r0 + oa + 1, a.D[1] - 1));
             }
-            float imw = 1.f;
-            if (weighted) imw = fmaxf(__fmul_rn(__fmul_rn(g0, __ldg(a.imap1 + r1)), w2), a.imap_floor);
-            float* dst = out_n + (long long)v * plane_vox + (long long)r1 * a.D[2];
+            uint4 rres[2][(CR + 7) / 8];
+            if (res) {
 #pragma unroll
-            for (int c = 0; c < CP; ++c)
-              if (c < c_real && !((a.abl & 1) && val[c] != 12345.f)) __stcs(dst + c * a.pl_cstride, weighted ? __fmul_rn(val[c], imw) : val[c]);
+              for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int pc = 0; pc < (CR + 7) / 8; ++pc)
+                  rres[h][pc] = *reinterpret_cast<const uint4*>(res_v + (size_t)((oa + h) * a.W) * 16 + (size_t)pc * a.GS * 16);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              if (h == 1 && !has_b) break;
+              if (r0 + oa + h >= a.D[1]) break;
+              float val[CP];
+#pragma unroll
+              for (int c = 0; c < CR; ++c) val[c] = __uint_as_float(acc[h][c]) + bias_r[c];
+              if (res) {
+#pragma unroll
+                for (int pc = 0; pc < (CR + 7) / 8; ++pc) {
+                  float rr[8];
+                  unpack8(rres[h][pc], rr);
+#pragma unroll
+                  for (int c = 0; c < 8; ++c)
+                    if (8 * pc + c < CR) val[8 * pc + c] += rr[c];
+                }
+              }
+              // importance weight with MONAI's roundings; the unweighted head multiplies by exactly 1.0
+              float imw = 1.f;
+              if (weighted) imw = fmaxf(__fmul_rn(__fmul_rn(g0, g1[h]), w2), floor_w);
+              float* dst = out_v + (long long)(oa + h) * a.D[2];
+#pragma unroll
+              for (int c = 0; c < CR; ++c, dst += cs) __stcs(dst, __fmul_rn(val[c], imw));
+            }
           }
         }
-        if (real && res_mode == 2 && ok) {
+        if (real && res && ok) {
           __syncwarp();
           if (lane == 0) mbar_arrive(PEMPTY(rslot));  // this warp no longer reads the plane
         }
         if (real && ++rslot == R) rslot = 0, rphase ^= 1u;  // ring entry / parity of the next real plane
+        fpar ^= 1u;
+        if (++slot3 == 3) slot3 = 0;
       }
     }
     if (tr && warp == 0 && lane == 0) a.trace[6] = wait_f, a.trace[7] = clock64() - te0;
   }
 
-  if (tr && warp < 4 && lane == 0) a.trace[8 + warp] = clock64();  // end of the epilogue warps of group 0
   tc_fence_before();
   __syncthreads();
   if (warp == PW) {
@@ -479,11 +550,8 @@ int rs_plan(int cp, const TcIO& io, RsPlan& pl) {
   SGM_REQUIRE(bt1 > 0, SGM_ERR_UNSUPPORTED, "rs_plan: no strip height fits shared memory");
   a.t1 = bt1, a.H1 = bt1 + 2, a.R = std::min(bR, 4);
   a.GS = round_up(a.H1 * a.W, 8);
-  a.RC = 4;  // = the number of epilogue groups: the rows a commit releases go to four different groups
-  if (const char* env = getenv("SGM_RS_RC")) a.RC = std::max(1, std::min(16, atoi(env)));
-  a.rc_log2 = 0;
-  while ((2 << a.rc_log2) <= a.RC) ++a.rc_log2;
-  a.RC = 1 << a.rc_log2;
+  a.issuers = 1;
+  if (const char* env = getenv("SGM_RS_ISSUERS")) a.issuers = atoi(env) == 2 ? 2 : 1;
   a.nstrips = ceil_div(a.D[1], bt1);
   a.nunits = a.nstrips * io.n;
   pl.smem_bytes = fixed + a.R * 2 * a.GS * 16;
@@ -497,7 +565,6 @@ int rs_plan(int cp, const TcIO& io, RsPlan& pl) {
 int rs_pack(const sgm_conv_desc& d, TcConv* c) {
   c->rs_cp = 0;
   if (getenv("SGM_NO_RS")) return SGM_OK;
-  if (!getenv("SGM_RS")) return SGM_OK;  // opt-in while the plane-sweep kernel is as fast (profiles/r01c_rs_notes.md)
   if (d.kind != SGM_KIND_CONV || d.kernel != 3 || d.stride != 1 || c->flat0 || c->mode != MODE_S1) return SGM_OK;
   if (d.cout > 10 || d.cin > 16 || c->cgin != 2) return SGM_OK;
   const int cp = 10, NB = rs_nb(cp);
@@ -586,12 +653,21 @@ int rs_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t
   const int par[3] = {1, 1, 1};  // rank-5 map {8 ch, D2, D1, D0, n * groups}: a row of W positions exceeds the 256-element box of the merged form
   int rc = make_brick_map(&tm, io.in0, io.n * io.cg0, io.id, box, par);
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SGM_CUDA_CHECK(cudaFuncSetAttribute(rs_conv_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRsSmemMax));
-    attr_set = true;
+  rc = SGM_ERR_UNSUPPORTED;
+#define SGM_RS_CASE(CRV)                                                                                              \
+  if (a.c_real == CRV) {                                                                                              \
+    static bool attr_set = false;                                                                                     \
+    if (!attr_set) {                                                                                                  \
+      SGM_CUDA_CHECK(cudaFuncSetAttribute(rs_conv_kernel<10, CRV>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRsSmemMax)); \
+      attr_set = true;                                                                                                \
+    }                                                                                                                 \
+    rs_conv_kernel<10, CRV><<<pe->grid, kRsThreads, pe->smem_bytes, st>>>(a, tm);                                     \
+    rc = SGM_OK;                                                                                                      \
   }
-  rs_conv_kernel<10><<<pe->grid, kRsThreads, pe->smem_bytes, st>>>(a, tm);
+  SGM_RS_CASE(1) SGM_RS_CASE(2) SGM_RS_CASE(3) SGM_RS_CASE(4) SGM_RS_CASE(5) SGM_RS_CASE(6) SGM_RS_CASE(7) SGM_RS_CASE(8)
+  SGM_RS_CASE(9) SGM_RS_CASE(10)
+#undef SGM_RS_CASE
+  SGM_REQUIRE(rc == SGM_OK, SGM_ERR_UNSUPPORTED, "rs_launch: no instantiation for %d output channels", a.c_real);
   SGM_CUDA_CHECK(cudaGetLastError());
   if (trace_on) {
     long long t[32];
@@ -601,7 +677,7 @@ int rs_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t
     fprintf(stderr,
             "[rs trace] D=(%d,%d,%d) n=%d t1=%d RC=%d units/cta=%.0f | issuer: start %lld end %lld (%.0f clk / input row), waited %lld "
             "for planes, %lld for cleared rows | epilogue warp 0: %lld clk, waited %lld for MMAs | kernel %lld clk\n",
-            a.D[0], a.D[1], a.D[2], io.n, a.t1, a.RC, units, t[1] - t[0], t[2] - t[0], (double)(t[2] - t[1]) / rows, t[3], t[4],
+            a.D[0], a.D[1], a.D[2], io.n, a.t1, 4, units, t[1] - t[0], t[2] - t[0], (double)(t[2] - t[1]) / rows, t[3], t[4],
             t[7], t[6], t[5] - t[0]);
   }
   return SGM_OK;

@@ -15,7 +15,6 @@ from segmantic_b200.synthetic import synthetic_state_dict, synthetic_volume  # n
 def make_nets(cout, dev):
     sd = synthetic_state_dict(3, 1, cout, seed=0)
     os.environ.pop("SGM_NO_RS", None)
-    os.environ["SGM_RS"] = "1"
     rs = engine.UNetB200(sd, spatial_dims=3, in_channels=1, out_channels=cout, device=dev, precision="bf16")
     os.environ["SGM_NO_RS"] = "1"
     ps = engine.UNetB200(sd, spatial_dims=3, in_channels=1, out_channels=cout, device=dev, precision="bf16")

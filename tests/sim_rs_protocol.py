@@ -20,18 +20,19 @@ class MBar:
     def try_wait(self, parity):
         return (self.phase & 1) != parity   # phase with this parity has completed
 
-def run(D0, t1, R, nq, units, seed, res=True, verbose=False, RC=4):
+def run(D0, t1, R, nq, units, seed, res=True, verbose=False, RC=4, ni=1):
     rnd = random.Random(seed)
     H1 = t1 + 2   # RC: input rows per tcgen05.commit (one 'chunk multiplied' barrier per chunk and plane)
     PFULL = [MBar(1, f"PFULL{s}") for s in range(R)]
-    PEMPTY = [MBar(1 + (4 * nq if res else 0), f"PEMPTY{s}") for s in range(R)]
-    FULL = [MBar(1, f"FULL{i}") for i in range(H1)]
-    CLR = [MBar(nq, f"CLR{o}") for o in range(t1)]
-    mma_queue = []   # in-order tensor pipe: list of ('mma', tag) / ('commit', bar)
+    PEMPTY = [MBar(ni + (4 * nq if res else 0), f"PEMPTY{s}") for s in range(R)]   # every issuer warp commits
+    FULL = [MBar(ni, f"FULL{c}") for c in range((H1 + 3) // 4)]   # per chunk of four input rows, both issuers commit
+    CLR = [MBar(nq * max(min(4, t1 - 4 * c), 1), f"CLR{c}") for c in range((t1 + 3) // 4)]   # per chunk of four output rows
+    mma_queues = [[], []]   # per issuer thread, in order: ('mma', tag) / ('commit', bar); the pipe interleaves them
     tma_queue = []   # pending loads: bar
     # ground truth tracking for hazards
     state = dict(mma_done=set(), cleared={}, true_phase={})
     errors = []
+    seen = {}
 
     def producer():
         G = 0
@@ -45,7 +46,8 @@ def run(D0, t1, R, nq, units, seed, res=True, verbose=False, RC=4):
                 G += 1
                 yield None
 
-    def issuer():
+    def issuer(iw):
+        mma_queue = mma_queues[iw]
         G = 0
         for kl in range(units):
             for xi in range(D0 + 2):
@@ -54,19 +56,27 @@ def run(D0, t1, R, nq, units, seed, res=True, verbose=False, RC=4):
                 real = xi < D0
                 if real:
                     slot = G % R
-                    while not PFULL[slot].try_wait((G // R) & 1): yield ("wait", f"iss PFULL{slot} G={G}")
+                    while not PFULL[slot].try_wait((G // R) & 1): yield ("wait", f"iss{iw} PFULL{slot} G={G}")
                     if ("loaded", G) not in state["mma_done"]: errors.append(f"issuer passed PFULL before plane {G} loaded")
-                for i in range(H1):
-                    if Vc >= 0 and i < t1:
-                        while not CLR[i].try_wait(Vc & 1): yield ("wait", f"iss CLR{i} Vc={Vc}")
-                        # ground truth: all nq warps cleared (Vc, i)
-                        if state["cleared"].get((Vc, i), 0) != nq: errors.append(f"issuer passed CLR[{i}] Vc={Vc} with {state['cleared'].get((Vc,i),0)} clears")
-                    chunk_end = (i + 1) % RC == 0 or i + 1 == H1
+                next_commit = 0
+                for i in range(iw, H1, ni):
+                    c = i >> 2
+                    if Vc >= 0 and (i & 3) == iw and 4 * c < t1:
+                        while not CLR[c].try_wait(Vc & 1): yield ("wait", f"iss{iw} CLR{c} Vc={Vc}")
+                        for o in range(4 * c, min(4 * c + 4, t1)):
+                            if state["cleared"].get((Vc, o), 0) != nq: errors.append(f"issuer{iw} passed CLR[{c}] Vc={Vc}: row {o} has {state['cleared'].get((Vc,o),0)} clears")
+                        seen.setdefault((iw, Vc), set()).update(range(4 * c, min(4 * c + 4, t1)))
+                    if Vc >= 0:
+                        for o in range(max(i - 2, 0), min(i, t1 - 1) + 1):
+                            if o not in seen.get((iw, Vc), set()): errors.append(f"issuer{iw} row {i} touches unobserved row {o}")
                     if real:
                         mma_queue.append(("mma", (G, i)))
-                    if chunk_end:
-                        mma_queue.append(("commit", FULL[i // RC]))
+                    if (i & 3) == 4 - ni + iw or i + ni >= H1:
+                        mma_queue.append(("commit", FULL[c]))
+                        next_commit = c + 1
                     yield None
+                for c in range(next_commit, ((H1 - 1) >> 2) + 1):
+                    mma_queue.append(("commit", FULL[c]))
                 if real:
                     mma_queue.append(("commit", PEMPTY[slot]))
                     G += 1
@@ -85,14 +95,17 @@ def run(D0, t1, R, nq, units, seed, res=True, verbose=False, RC=4):
                     rslot = Gres % R
                     while not PFULL[rslot].try_wait((Gres // R) & 1): yield ("wait", f"epi{g}{q} PFULL{rslot} Gres={Gres}")
                     if ("loaded", Gres) not in state["mma_done"]: errors.append(f"epi passed PFULL before plane {Gres} loaded")
-                for o in range(g, t1, 4):
-                    ilast = (o + 2) // RC
+                for oa in range(2 * g, t1, 8):       # two adjacent output rows per step
+                    rows = [oa] + ([oa + 1] if oa + 1 < t1 else [])
+                    ilast = (rows[-1] + 2) >> 2
                     while not FULL[ilast].try_wait(Gv & 1): yield ("wait", f"epi{g}{q} FULL{ilast} Gv={Gv} v={v}")
-                    for i in range(o, o + 3):
-                        if (Gin, i) not in state["mma_done"]: errors.append(f"epi{g}{q} passed FULL[{ilast}] before MMA({Gin},{i}) done (v={v}, o={o})")
+                    for o in rows:
+                        for i in range(o, o + 3):
+                            if (Gin, i) not in state["mma_done"]: errors.append(f"epi{g}{q} passed FULL[{ilast}] before MMA({Gin},{i}) done (v={v}, o={o})")
                     yield None
-                    state["cleared"][(V, o)] = state["cleared"].get((V, o), 0) + 1
-                    CLR[o].arrive()
+                    for o in rows:
+                        state["cleared"][(V, o)] = state["cleared"].get((V, o), 0) + 1
+                        CLR[o >> 2].arrive()
                     yield None
                 if real and res:
                     PEMPTY[rslot].arrive()
@@ -101,8 +114,9 @@ def run(D0, t1, R, nq, units, seed, res=True, verbose=False, RC=4):
     def pipe():   # tensor pipe + TMA engine: complete queued work in order, at random times
         while True:
             did = False
-            if mma_queue and rnd.random() < 0.7:
-                kind, x = mma_queue.pop(0)
+            qs = [q for q in mma_queues if q]
+            if qs and rnd.random() < 0.7:
+                kind, x = rnd.choice(qs).pop(0)
                 if kind == "mma": state["mma_done"].add(x)
                 else: x.arrive()
                 did = True
@@ -113,7 +127,9 @@ def run(D0, t1, R, nq, units, seed, res=True, verbose=False, RC=4):
                 did = True
             yield None if did else ("idle", "pipe")
 
-    procs = {"prod": producer(), "iss": issuer(), "pipe": pipe()}
+    procs = {"prod": producer(), "pipe": pipe()}
+    for iw in range(ni):
+        procs[f"iss{iw}"] = issuer(iw)
     for g in range(4):
         for q in range(nq):
             procs[f"epi{g}{q}"] = epi(g, q)
@@ -132,7 +148,7 @@ def run(D0, t1, R, nq, units, seed, res=True, verbose=False, RC=4):
         status[k] = r
         if steps % 2000 == 0:
             # deadlock check: everyone alive is waiting and pipe idle and queues empty
-            if not mma_queue and not tma_queue and all(isinstance(status.get(n), tuple) for n in procs):
+            if not any(mma_queues) and not tma_queue and all(isinstance(status.get(n), tuple) for n in procs):
                 # run a sweep: poll everyone once more to confirm
                 stuck = True
                 for n in list(procs):
@@ -140,7 +156,7 @@ def run(D0, t1, R, nq, units, seed, res=True, verbose=False, RC=4):
                     except StopIteration: alive.discard(n); del procs[n]; stuck = False; continue
                     status[n] = r
                     if not isinstance(r, tuple): stuck = False
-                if stuck and not mma_queue and not tma_queue:
+                if stuck and not any(mma_queues) and not tma_queue:
                     return "DEADLOCK", {n: status[n][1] for n in procs if n != "pipe"}, errors
         if errors: return "HAZARD", errors[:5], None
     return "OK", steps, errors
@@ -149,7 +165,7 @@ if __name__ == "__main__":
     bad = 0
     for seed in range(int(sys.argv[1]) if len(sys.argv) > 1 else 40):
         for (D0, t1, R, nq, units) in ((6, 3, 4, 3, 1), (6, 3, 4, 3, 2), (8, 9, 4, 3, 3), (5, 6, 3, 4, 2), (7, 12, 4, 3, 2)):
-            r = run(D0, t1, R, nq, units, seed)
+            r = run(D0, t1, R, nq, units, seed, ni=1 + seed % 2)
             if r[0] != "OK":
                 bad += 1
                 print(seed, (D0, t1, R, nq, units), r[0], r[1])

@@ -12,3 +12,14 @@ def test_tc_layers_match_cuda_core_kernels(cuda_device, group):
 
     results = diag_tc_layers.run(group)
     assert results and all(results), f"{sum(results)}/{len(results)} cases passed in group {group}"
+
+
+def test_row_sweep_head_matches_plane_sweep(cuda_device):
+    """The row-sweep head kernel (conv_rs.cu: d0 and d1 taps folded into MMA N through overlapping accumulator
+    columns) against the plane-sweep kernel (SGM_NO_RS=1) on identical inputs: whole-network forwards and
+    sliding-window predictions, full / partial strips, 3 and 4 lane quarters, one and several units per CTA.
+    Only the fp32 accumulation order differs: <= 2e-5 of the logit range."""
+    from tests import diag_rs_head
+
+    results = diag_rs_head.run()
+    assert results and all(results), f"{sum(results)}/{len(results)} cases passed"
