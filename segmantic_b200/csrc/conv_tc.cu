@@ -37,6 +37,17 @@ namespace {
 
 constexpr int kThreads = 192;
 constexpr int kSmemBudget = 110 * 1024;   // two CTAs per SM
+
+// CTAs per SM the launch plan aims for (SGM_TC_CTAS = 2 or 3): the one-CTA-per-brick kernel is latency bound (TMEM
+// allocation, brick TMA, weight ring, 27-108 MMAs, epilogue in sequence), so what counts is how many bricks overlap.
+static int target_ctas() {
+  static int v = 0;
+  if (!v) {
+    v = 3;
+    if (const char* env = getenv("SGM_TC_CTAS")) v = atoi(env) == 2 ? 2 : 3;
+  }
+  return v;
+}
 using namespace tcptx;
 
 struct KArgs {
@@ -93,8 +104,10 @@ __constant__ uint32_t c_blk[kBlkConst];
 
 
 // ACH: the brick is streamed in channel chunks (deep layers, one CTA per SM); compiled out of the common path
-template <bool ACH>
-__global__ void __launch_bounds__(kThreads, ACH ? 1 : 2)
+// MINB = CTAs per SM the register allocation aims for: 2 (168 registers) or 3 (96 registers, a few spills in the
+// epilogue) -- chosen per layer by the launch plan (tc_launch)
+template <bool ACH, int MINB = 2>
+__global__ void __launch_bounds__(kThreads, ACH ? 1 : MINB)
 tc_conv_kernel(const KArgs a, const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -968,7 +981,7 @@ int make_brick_map(CUtensorMap* out, const void* ptr, int ncg, const int d[3], c
 
 // Geometry of one launch (tile shape search, TMEM / weight-ring sizing): depends only on the conv and the
 // tensor extents, so it is computed once per (conv, dims, batch) and cached.
-static int tc_plan(const TcConv& c, const TcIO& io, KArgs& a, int& smem_bytes_out) {
+static int tc_plan(const TcConv& c, const TcIO& io, KArgs& a, int& smem_bytes_out, int ctas) {
   memset(&a, 0, sizeof(a));
   SGM_REQUIRE(io.cg0 + io.cg1 == c.cgin, SGM_ERR_INVALID, "tc_launch: input channel groups %d+%d != %d", io.cg0,
               io.cg1, c.cgin);
@@ -983,9 +996,10 @@ static int tc_plan(const TcConv& c, const TcIO& io, KArgs& a, int& smem_bytes_ou
   const int NB = c.mma_n;
   a.mmaN = NB;
   // weight ring
-  a.G = std::max(1, std::min(nblk, 16384 / (NB * 32)));
+  const bool three = ctas == 3 && !c.kmajor;
+  a.G = std::max(1, std::min(nblk, (three ? 8192 : 16384) / (NB * 32)));
   a.ngroups = ceil_div(nblk, a.G);
-  a.nstages = std::min(a.G * NB * 32 <= 8192 ? 6 : 4, a.ngroups);
+  a.nstages = std::min(three ? 3 : (a.G * NB * 32 <= 8192 ? 6 : 4), a.ngroups);
   a.resident = a.ngroups <= a.nstages;
   a.w_stage_bytes = round_up(a.G * NB * 32, 128);
   // TMEM
@@ -1090,7 +1104,7 @@ static int tc_plan(const TcConv& c, const TcIO& io, KArgs& a, int& smem_bytes_ou
         const int rl = ((a.lo[0] + t[0] - 1) * H[1] + a.lo[1] + t[1] - 1) * H[2] + a.lo[2] + t[2] - 1;
         const int ntl = ceil_div(rl - rf + 1, 128);
         const int units = a.nslab * c.cgin * P + 128 + 2 * (H[1] * H[2] + H[2] + 2);
-        if ((long long)units * 16 + fixed_bytes > kSmemBudget) continue;
+        if ((long long)units * 16 + fixed_bytes > (ctas == 3 ? 74 * 1024 : kSmemBudget)) continue;
         const long long nct = (long long)ceil_div(a.rd[0], t[0]) * ceil_div(a.rd[1], t[1]) * ceil_div(a.rd[2], t[2]) *
                               c.ncoblk * io.n;
         const double mma = (double)ntl * nblk * (34.0 + 0.36 * NB);
@@ -1098,7 +1112,7 @@ static int tc_plan(const TcConv& c, const TcIO& io, KArgs& a, int& smem_bytes_ou
         const double epi = (double)ntl * c.ncls * (N / 16) * 60.0;
         const double wload = (double)nblk * NB * 32 / 40.0;  // every CTA streams the whole filter bank from L2
         const double cta = std::max(std::max(mma, epi), wload) + load + 4000.0;
-        const double waves = (double)((nct + 295) / 296);
+        const double waves = (double)((nct + 148 * ctas - 1) / (148 * ctas));
         const double cost = waves * cta;
         if (cost < best) best = cost, bt[0] = t[0], bt[1] = t[1], bt[2] = t[2];
       }
@@ -1116,6 +1130,7 @@ static int tc_plan(const TcConv& c, const TcIO& io, KArgs& a, int& smem_bytes_ou
   a.tpc = std::min(a.tpc, a.ntiles);
   a.nchunks = ceil_div(a.ntiles, a.tpc);
   a.cols_per_buf = a.tpc * cols_tile;
+  if (a.nchunks == 1) a.nbuf = 1;  // a single chunk never uses the second accumulator buffer: half the TMEM columns
   int cols = a.nbuf * a.cols_per_buf, pw = 32;
   while (pw < cols) pw <<= 1;
   a.tmem_cols = pw;
@@ -1130,6 +1145,7 @@ struct PlanEntry {
   int key[8];
   KArgs args;
   int smem_bytes;
+  int ctas;
 };
 
 static void free_plans(void* p) { delete reinterpret_cast<std::vector<PlanEntry>*>(p); }
@@ -1148,7 +1164,14 @@ int tc_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t
   if (!pe) {
     PlanEntry e;
     memcpy(e.key, key, sizeof(key));
-    int rc = tc_plan(c, io, e.args, e.smem_bytes);
+    // three CTAs per SM where a tile's accumulators fit a third of the TMEM (<= 128 columns) and the brick plus a
+    // short weight ring fit 74 KB; otherwise two with the deeper ring (measured per layer: profiles/r01c_rs_notes.md 5)
+    e.ctas = target_ctas();
+    int rc = e.ctas == 3 ? tc_plan(c, io, e.args, e.smem_bytes, 3) : SGM_ERR_UNSUPPORTED;
+    if (rc || e.args.tmem_cols > 128 || e.args.achunk) {
+      e.ctas = 2;
+      rc = tc_plan(c, io, e.args, e.smem_bytes, 2);
+    }
     if (rc) return rc;
     plans->push_back(e);
     pe = &plans->back();
@@ -1184,6 +1207,7 @@ int tc_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t
   static bool attr_set = false;
   if (!attr_set) {
     SGM_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    SGM_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     SGM_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
@@ -1204,6 +1228,7 @@ int tc_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t
   }
   dim3 grid(a.nt[0] * a.nt[1] * a.nt[2], c.ncoblk, io.n);
   if (a.achunk) tc_conv_kernel<true><<<grid, kThreads, smem_bytes, st>>>(a, tm0, tm1);
+  else if (pe->ctas == 3) tc_conv_kernel<false, 3><<<grid, kThreads, smem_bytes, st>>>(a, tm0, tm1);
   else tc_conv_kernel<false><<<grid, kThreads, smem_bytes, st>>>(a, tm0, tm1);
   SGM_CUDA_CHECK(cudaGetLastError());
   if (trace_on) {
