@@ -522,6 +522,12 @@ def run_b200(args):
                               ms_per_launch=t * 1e3, algorithmic_bytes_per_launch=blend_bytes,
                               formula="4*C*n_windows*roi^3 (weighted logits read once) + 1*V (labels written)")
 
+    resample_roof = None
+    if world == 1 and not args.no_profile:
+        try:
+            resample_roof = resample_rooflines(dev, pk)
+        except Exception as e:  # noqa: BLE001  (diagnostic section: never lose the headline line)
+            log("resample rooflines failed:", repr(e))
     cpu = None
     if world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
@@ -544,7 +550,7 @@ def run_b200(args):
                 step_ms=dict(min=min(per_step), median=float(np.median(per_step)), max=max(per_step)),
                 regions_ms=[round(r[0], 3) for r in regions],
                 e2e=e2e, gpu_launches=int(launches_step * args.steps), clocks=clocks, roofline=roofline,
-                roofline_blend=blend_roof,
+                roofline_blend=blend_roof, roofline_resample=resample_roof,
                 cpu_baseline=cpu,
                 conv_stack=dict(ms_per_step=conv_ms, tflops=conv_tf, frac_bf16_peak=conv_tf / pk["bf16_sustained"],
                                 peak_tflops=pk["bf16_sustained"], layers=layers))
@@ -553,6 +559,83 @@ def run_b200(args):
         dist.destroy_process_group()
     return 0
 
+
+
+def resample_rooflines(dev, pk, iters=12):
+    """HBM rooflines of the resample kernels on the shapes of BASELINE configs[2] (512x512x120 @ 0.5x0.5x3 mm <-> 1 mm
+    isotropic 256x256x358): Spacing forward (trilinear), the fused inverse Spacing + argmax of 10-class logits, and the
+    ITK nearest-neighbour back-resample of a uint8 label map.  Outside the timed region of the headline metric; CUDA
+    events around every launch; inputs rotate over distinct buffers so that no launch finds its input in the 126 MB L2.
+    Algorithmic bytes: every input voxel read once + every output voxel written once."""
+    from segmantic_b200.seg import transforms as T
+
+    src_shape, dst_shape = (512, 512, 120), (256, 256, 358)
+    aff = np.diag([0.5, 0.5, 3.0, 1.0])
+    g = torch.Generator(device="cpu").manual_seed(3)
+    out = []
+
+    def timed(fn, nbuf):
+        fn(0)
+        torch.cuda.synchronize(dev)
+        ts = []
+        for i in range(iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn(i % nbuf)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ts.append(e0.elapsed_time(e1))
+        return float(np.median(ts))
+
+    def entry(kernel, ms, nbytes, formula):
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        return dict(kernel=kernel, bound="hbm", achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=gbs / pk["hbm"],
+                    ms_per_launch=ms, algorithmic_bytes_per_launch=nbytes, formula=formula, peak_source=pk["source"])
+
+    # 1. Spacingd forward: [1, 512, 512, 120] fp32 -> [1, 256, 256, 358]
+    nbuf = 6
+    imgs = [torch.randn((1,) + src_shape, generator=g).to(dev) for _ in range(nbuf)]
+    new_aff = T.zoom_affine(aff, (1.0, 1.0, 1.0))
+    shp, offset = T.compute_shape_offset(src_shape, aff, new_aff)
+    new_aff[:3, -1] = offset
+    assert tuple(shp) == dst_shape, shp
+    xf = np.linalg.solve(aff, new_aff)
+    ms = timed(lambda i: T.resample_index_affine(imgs[i], xf, dst_shape), nbuf)
+    out.append(entry("trilinear_kernel<false>[Spacingd 512x512x120 @0.5x0.5x3 -> 256x256x358 @1 mm, 1 channel; float64 arithmetic]", ms,
+                     4.0 * np.prod(src_shape) + 4.0 * np.prod(dst_shape), "4*V_in + 4*V_out"))
+    del imgs
+    # 2. inverse Spacing of 10-class logits fused with argmax: [10, 256, 256, 358] -> uint8 [512, 512, 120]
+    logits = [torch.randn((CLASSES,) + dst_shape, generator=g).to(dev) for _ in range(2)]
+    xinv = np.linalg.solve(new_aff, aff)
+    ms = timed(lambda i: T.resample_index_affine_argmax(logits[i], xinv, src_shape), 2)
+    out.append(entry("trilinear_brick_kernel<true>[inverse Spacing of 10-class logits + argmax -> 512x512x120 labels; float64 arithmetic]", ms,
+                     4.0 * CLASSES * np.prod(dst_shape) + 1.0 * np.prod(src_shape), "4*C*V_in + 1*V_out"))
+    del logits
+    # 3. ITK nearest-neighbour resample_to_ref of a uint8 label map: [256, 256, 358] @1 mm -> [512, 512, 120]
+    # (the C ABI directly: processing.resample_to_ref adds the [x,y,z] <-> C-order permute copies around the kernel)
+    import ctypes as C
+
+    from segmantic_b200 import _lib
+    lib = _lib.load()
+    labs = [torch.randint(0, CLASSES, tuple(reversed(dst_shape)), generator=g, dtype=torch.uint8).to(dev) for _ in range(nbuf)]
+    lout = torch.empty(tuple(reversed(src_shape)), dtype=torch.uint8, device=dev)
+
+    def dbl(a):
+        a = np.ascontiguousarray(a, dtype=np.float64).ravel()
+        return (C.c_double * a.size)(*a.tolist())
+
+    i2p, p2i, zero = dbl(np.diag([0.5, 0.5, 3.0])), dbl(np.eye(3)), dbl(np.zeros(3))
+
+    def itk(i):
+        with torch.cuda.device(dev):
+            _lib.check(lib.sgm_resample_itk(labs[i].data_ptr(), 0, _lib.i3(dst_shape), lout.data_ptr(), _lib.i3(src_shape),
+                                            i2p, zero, p2i, zero, 1, 0.0, int(torch.cuda.current_stream(dev).cuda_stream)),
+                       "sgm_resample_itk")
+
+    ms = timed(itk, nbuf)
+    out.append(entry("itk_resample_vec_kernel<uint8,4>[nearest resample_to_ref of labels 256x256x358 -> 512x512x120; float64 index arithmetic]", ms,
+                     1.0 * np.prod(dst_shape) + 1.0 * np.prod(src_shape), "1*V_in + 1*V_out"))
+    return out
 
 def main():
     ap = argparse.ArgumentParser()
