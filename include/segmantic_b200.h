@@ -13,6 +13,8 @@
  *   sgm_resample_itk                     <- sitk.ResampleImageFilter           image/processing.py:60-70, 87-97
  *   sgm_normalize_intensity / sgm_foreground_bbox
  *                                        <- NormalizeIntensityd/CropForegroundd seg/monai_unet.py:163-169
+ *   sgm_confusion_matrix                 <- confusion_matrix + DiceMetric / ConfusionMatrixMetric inputs
+ *                                                                               seg/evaluation.py:96-125, seg/monai_unet.py:640-725
  *
  * Conventions: every pointer named *_dev is a device pointer on the CURRENT CUDA device; the caller
  * (PyTorch in the Python host) owns all device buffers including the workspace; the library owns
@@ -205,6 +207,13 @@ SGM_API int32_t sgm_normalize_intensity(const float* in_dev, float* out_dev, int
  * bbox_dev: int32[6] = {lo0,lo1,lo2,hi0,hi1,hi2} (hi exclusive; empty -> all zeros). */
 SGM_API int32_t sgm_foreground_bbox(const float* in_dev, int32_t channels, const int32_t dims[3],
                             int32_t* bbox_dev, void* stream);
+
+/* Evaluation branch of predict() (seg/monai_unet.py:672-704; seg/evaluation.py:96-125): confusion matrix of two uint8
+ * label maps, cm[t * num_classes + p] = #{voxels with true label t and predicted label p} (rows = y, columns =
+ * y_pred: the convention of sklearn.metrics.confusion_matrix the reference's docstring names).  Pairs with a label
+ * >= num_classes are not counted; their number is written to ignored_dev (may be NULL).  num_classes <= 64. */
+SGM_API int32_t sgm_confusion_matrix(const uint8_t* y_pred_dev, const uint8_t* y_dev, int64_t voxels,
+                                     int32_t num_classes, int64_t* cm_dev, int64_t* ignored_dev, void* stream);
 
 #ifdef __cplusplus
 }

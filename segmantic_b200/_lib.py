@@ -90,6 +90,8 @@ SIGNATURES = {
     "sgm_normalize_intensity": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p,
                                             C.c_void_p]),
     "sgm_foreground_bbox": (C.c_int32, [C.c_void_p, C.c_int32, _I3, C.c_void_p, C.c_void_p]),
+    "sgm_confusion_matrix": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+                                         C.c_void_p]),
 }
 
 _lib = None

@@ -253,32 +253,60 @@ def predict(model_file: Path, test_images: List[Path], test_labels: Optional[Lis
     if output_dir:
         os.makedirs(output_dir, exist_ok=True)
     have_labels = test_labels is not None and len(test_labels) == len(test_images) and len(test_labels) > 0
-    all_mean_dice = []
+    from . import evaluation as E
+
+    def print_table(header, vals, indent="\t"):
+        print(indent + "\t".join(header).expandtabs(30))
+        print(indent + "\t".join(f"{x}" for x in vals).expandtabs(30))
+
+    # evaluation state (monai_unet.py:640-646): DiceMetric(include_background=False, reduction="mean"),
+    # ConfusionMatrixMetric([sensitivity, specificity, precision, accuracy]), CumulativeAverage of the class Dice
+    all_mean_dice: List[float] = []       # dice_metric.aggregate() after every image (running mean over images)
+    image_mean_dice: List[float] = []
+    class_dice_sum = np.zeros(max(num_classes - 1, 0))
+    class_dice_cnt = np.zeros(max(num_classes - 1, 0))
+    all_counts = []
     for i, img_path in enumerate(test_images):
         img_path = Path(img_path)
         image, affine, header = nifti.read(img_path)  # [C, X, Y, Z] float32, RAS affine
-        lab = predict_volume(net, torch.from_numpy(image), affine, spacing, overlap=overlap, mode=mode,
-                             sw_batch_size=sw_batch_size, precision=precision, invert=invert)
+        lab_dev = predict_volume(net, torch.from_numpy(image), affine, spacing, overlap=overlap, mode=mode,
+                                 sw_batch_size=sw_batch_size, precision=precision, invert=invert, return_device=True)
+        name = img_path.name
+        for ext in (".nii.gz", ".nii", ".nrrd", ".mha", ".mhd"):
+            if name.endswith(ext):
+                name = name[: -len(ext)]
+                break
         if output_dir:
-            name = img_path.name
-            for ext in (".nii.gz", ".nii", ".nrrd", ".mha", ".mhd"):
-                if name.endswith(ext):
-                    name = name[: -len(ext)]
-                    break
-            nifti.write(Path(output_dir) / f"{name}.nii.gz", lab.numpy().astype(np.float32), affine)
+            nifti.write(Path(output_dir) / f"{name}.nii.gz", lab_dev.cpu().numpy().astype(np.float32), affine)
         if have_labels:
             ref_lab, _, _ = nifti.read(Path(test_labels[i]))
-            ref_lab = torch.from_numpy(ref_lab[0]).long()
-            dice = []
-            for c in range(1, num_classes):  # include_background=False
-                a, b = (lab.long() == c), (ref_lab == c)
-                den = int(a.sum()) + int(b.sum())
-                dice.append(float("nan") if den == 0 else 2.0 * int((a & b).sum()) / den)
-            print(img_path.name)
-            print("\t" + "\t".join(tissue_names[1:]).expandtabs(30))
-            print("\t" + "\t".join(f"{x}" for x in dice).expandtabs(30))
-            all_mean_dice.append(float(np.nanmean(dice)) if dice else float("nan"))
-    if have_labels and output_dir:
-        out = Path(output_dir) / f"mean_dice_{model_file.stem}_generalized_score.txt"
-        with out.open("w") as f:
-            print(f"Mean dice: {np.nanmean(all_mean_dice)}", file=f)
+            ref_dev = torch.from_numpy(np.ascontiguousarray(ref_lab[0])).to(lab_dev.device)
+            if tuple(ref_dev.shape) != tuple(lab_dev.shape):
+                raise ValueError(f"label {test_labels[i]} has shape {tuple(ref_dev.shape)}, prediction {tuple(lab_dev.shape)}")
+            cm = E.confusion_matrix(num_classes, lab_dev, ref_dev)   # one pass over both label maps on the device
+            dice = E.class_dice(cm, include_background=False)
+            valid = ~np.isnan(dice)
+            class_dice_sum[valid] += dice[valid]
+            class_dice_cnt[valid] += 1
+            all_counts.append(E.confusion_counts(cm))
+            image_mean_dice.append(float(np.nanmean(dice)) if valid.any() else float("nan"))
+            print("Mean Dice: ", image_mean_dice[-1])
+            print("Class Dice:")
+            print_table(tissue_names[1:], dice)
+            all_mean_dice.append(float(np.nanmean(image_mean_dice)))
+            if output_dir:
+                # the reference plots <base>_confusion.png (matplotlib, out of scope); the matrix itself is kept
+                np.savetxt(Path(output_dir) / f"{name}_confusion.csv", cm, fmt="%d", delimiter=",")
+    if output_dir is None:
+        print("No output path specified, dice scores won't be saved.")
+    else:
+        np.savetxt(Path(output_dir) / f"mean_dice_{model_file.stem}_generalized_score.txt", all_mean_dice, delimiter=",")
+    if have_labels:
+        print("*" * 80)
+        print("Total Mean Dice: ", all_mean_dice[-1] if all_mean_dice else float("nan"))
+        print("Total Class Dice:")
+        with np.errstate(invalid="ignore", divide="ignore"):
+            print_table(tissue_names[1:], class_dice_sum / class_dice_cnt)
+        print("Total Conf. Matrix Metrics:")
+        metrics = E.confusion_metrics(all_counts)
+        print_table(list(E.CONFUSION_METRICS), [metrics[k] for k in E.CONFUSION_METRICS])

@@ -174,3 +174,18 @@ def test_golden_predict_and_itk():
     assert np.array_equal(oitk.resample(img, (0.25, 0.3, 0.35), False).array, GOLD["itk_lin"])
     ref = oitk.Image(np.zeros((12, 10, 7), np.uint16), (0.25, 0.3, 0.35), (1.3, -2.1, 0.75))
     assert np.array_equal(oitk.resample_to_ref(img, ref, True).array, GOLD["itk_ref"])
+
+
+def test_evaluation_oracle_known_answers():
+    """confusion matrix / Dice / MONAI confusion-matrix metrics on a hand-checked example (8 voxels, 3 classes)."""
+    from oracle import evaluation as oe
+    y = np.array([0, 0, 1, 1, 2, 2, 2, 1])
+    p = np.array([0, 1, 1, 1, 2, 0, 2, 2])
+    cm = oe.confusion_matrix(3, p, y)
+    assert np.array_equal(cm, [[1, 1, 0], [0, 2, 1], [1, 0, 2]])           # rows: truth, columns: prediction
+    assert np.allclose(oe.class_dice(cm), [2 * 2 / (3 + 3), 2 * 2 / (3 + 3)])
+    counts = oe.confusion_counts(cm)                                         # (tp, fp, tn, fn) per class
+    assert np.array_equal(counts, [[1, 1, 5, 1], [2, 1, 4, 1], [2, 1, 4, 1]])
+    m = oe.confusion_metrics([counts])
+    assert m == {"sensitivity": 5 / 8, "specificity": 13 / 16, "precision": 5 / 8, "accuracy": 18 / 24}
+    assert np.array_equal(oe.confusion_matrix(2, np.array([0, 1, 7]), np.array([1, 1, 0])), [[0, 0], [1, 1]])
