@@ -123,3 +123,35 @@ def test_row_sweep_head_is_deterministic_and_batch_independent(cuda_device, monk
     ref = eng.sliding_window_inference(vol, roi, 1, ps, overlap=0.5, mode="gaussian")
     ps.check()
     assert rel_err(outs[0], ref) < 2e-5
+
+
+def test_config2_full_size_properties(cuda_device, monkeypatch):
+    """BASELINE configs[1] at FULL size (256^3 volume, 10 tissues, roi 96^3, overlap 0.5, Gaussian, bf16: 125 windows,
+    far beyond what the CPU oracle finishes in seconds) through size-independent properties:
+    repeatability, independence of the device window batch, deferred == read-modify-write blend, and agreement of the
+    two head kernels outside argmax near-ties."""
+    eng = _engine()
+    _, sd = make_oracle_net(3, 1, 10, seed=0)
+    vol = normalized_volume((256, 256, 256), seed=1)[None].to(cuda_device)
+    roi = (96, 96, 96)
+    kw = dict(overlap=0.5, mode="gaussian", return_labels=True, return_logits=False)
+    net = eng.UNetB200(sd, spatial_dims=3, in_channels=1, out_channels=10, device=cuda_device, precision="bf16")
+    a = eng.sliding_window_inference(vol, roi, 4, net, **kw)["labels"]
+    net.check()
+    assert a.shape == (1, 1, 256, 256, 256) and int(a.max()) < 10
+    assert torch.equal(eng.sliding_window_inference(vol, roi, 4, net, **kw)["labels"], a)      # run to run
+    monkeypatch.setenv("SGM_SW_BATCH", "24")
+    assert torch.equal(eng.sliding_window_inference(vol, roi, 4, net, **kw)["labels"], a)      # 6 launches instead of 1
+    monkeypatch.delenv("SGM_SW_BATCH")
+    # plane-sweep head: the deferred blend and MONAI's sequential read-modify-write agree bit for bit at full size
+    monkeypatch.setenv("SGM_NO_RS", "1")
+    ps = eng.UNetB200(sd, spatial_dims=3, in_channels=1, out_channels=10, device=cuda_device, precision="bf16")
+    monkeypatch.delenv("SGM_NO_RS")
+    monkeypatch.setenv("SGM_BLEND", "gather")
+    g = eng.sliding_window_inference(vol, roi, 4, ps, **kw)["labels"]
+    monkeypatch.setenv("SGM_BLEND", "rmw")
+    r = eng.sliding_window_inference(vol, roi, 4, ps, **kw)["labels"]
+    ps.check()
+    assert torch.equal(g, r)
+    # the two head kernels differ only in the fp32 summation order inside the conv: labels flip at near-ties only
+    assert float((g != a).float().mean()) < 1e-4
