@@ -13,6 +13,9 @@
  *   sgm_resample_itk                     <- sitk.ResampleImageFilter           image/processing.py:60-70, 87-97
  *   sgm_normalize_intensity / sgm_foreground_bbox
  *                                        <- NormalizeIntensityd/CropForegroundd seg/monai_unet.py:163-169
+ *   sgm_ensemble_mean_argmax / _vote / _select_best
+ *                                        <- MeanEnsembled / VoteEnsembled / SelectBestEnsembled + AsDiscreted
+ *                                                                               seg/monai_unet.py:848-1004, seg/transforms.py:15-61
  *   sgm_confusion_matrix                 <- confusion_matrix + DiceMetric / ConfusionMatrixMetric inputs
  *                                                                               seg/evaluation.py:96-125, seg/monai_unet.py:640-725
  *
@@ -214,6 +217,20 @@ SGM_API int32_t sgm_foreground_bbox(const float* in_dev, int32_t channels, const
  * >= num_classes are not counted; their number is written to ignored_dev (may be NULL).  num_classes <= 64. */
 SGM_API int32_t sgm_confusion_matrix(const uint8_t* y_pred_dev, const uint8_t* y_dev, int64_t voxels,
                                      int32_t num_classes, int64_t* cm_dev, int64_t* ignored_dev, void* stream);
+
+/* Ensemble combination (seg/monai_unet.py:848-1004, seg/transforms.py:15-61), voxel-wise over stacked model outputs:
+ *   mean:        logits [E][C][V] float32 -> mean_m(x_m * w_m / mean(w)) (MONAI MeanEnsemble; weights NULL = equal; host
+ *                array) -> argmax labels (ties -> lowest class); mean_dev (may be NULL) receives the [C][V] mean.
+ *   vote:        labels [E][V] uint8 -> majority class (MONAI VoteEnsemble(num_classes): ties -> lowest class).
+ *   select_best: labels [E][V] uint8 + (tissue id, model index) pairs in dictionary order -> voxels the chosen model
+ *                labels `tissue` get `tissue`, later pairs overwrite earlier ones, unclaimed voxels are 0. */
+SGM_API int32_t sgm_ensemble_mean_argmax(const float* logits_dev, int32_t n_models, int32_t num_classes, int64_t voxels,
+                                         const float* weights, uint8_t* labels_dev, float* mean_dev, void* stream);
+SGM_API int32_t sgm_ensemble_vote(const uint8_t* labels_in_dev, int32_t n_models, int32_t num_classes, int64_t voxels,
+                                  uint8_t* labels_out_dev, void* stream);
+SGM_API int32_t sgm_ensemble_select_best(const uint8_t* labels_in_dev, int32_t n_models, int64_t voxels,
+                                         const int32_t* tissue_ids, const int32_t* model_ids, int32_t n_pairs,
+                                         uint8_t* labels_out_dev, void* stream);
 
 #ifdef __cplusplus
 }

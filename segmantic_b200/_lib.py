@@ -90,6 +90,11 @@ SIGNATURES = {
     "sgm_normalize_intensity": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p,
                                             C.c_void_p]),
     "sgm_foreground_bbox": (C.c_int32, [C.c_void_p, C.c_int32, _I3, C.c_void_p, C.c_void_p]),
+    "sgm_ensemble_mean_argmax": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_float), C.c_void_p,
+                                             C.c_void_p, C.c_void_p]),
+    "sgm_ensemble_vote": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
+    "sgm_ensemble_select_best": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                             C.c_int32, C.c_void_p, C.c_void_p]),
     "sgm_confusion_matrix": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                          C.c_void_p]),
 }

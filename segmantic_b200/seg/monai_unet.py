@@ -125,7 +125,8 @@ def _infer_io_channels(sd, hp) -> dict:
 def predict_volume(net: Net, image: torch.Tensor, affine: Optional[np.ndarray] = None,
                    spacing: Sequence[float] = (), *, overlap: float = 0.25, mode: str = "constant",
                    sw_batch_size: int = 4, precision: str = "fp32", invert: str = "logits",
-                   normalize: bool = True, crop_foreground: bool = True, return_device: bool = False):
+                   normalize: bool = True, crop_foreground: bool = True, return_device: bool = False,
+                   ensemble: Optional[dict] = None):
     """The array-level core of ``predict()`` (``monai_unet.py:589-670``) for ONE image.
 
     ``image``: ``[C, X, Y, Z]`` (``[C, X, Y]`` for 2-D networks) in ITK index order, any device (host
@@ -172,9 +173,14 @@ def predict_volume(net: Net, image: torch.Tensor, affine: Optional[np.ndarray] =
     if len(spacing) and nd == 3:
         img, aff, record = T.spacing_forward(img, aff, spacing)
     net_in = img if nd == 3 else img[:, 0]
-    want_labels = record is None or invert == "labels"
-    res = sliding_window_inference(net_in.unsqueeze(0), net.spatial_size, sw_batch_size, eng, overlap=overlap,
-                                   mode=mode, return_labels=want_labels, return_logits=not want_labels)
+    want_labels = record is None or invert == "labels" or ensemble is not None
+    if ensemble is not None:
+        # several models over the same pre-processed volume, combined on the network grid (ensemble_creator)
+        from . import ensemble as ENS
+        res = {"labels": ENS.combine(ensemble, net_in.unsqueeze(0), sw_batch_size, precision, overlap, mode)}
+    else:
+        res = sliding_window_inference(net_in.unsqueeze(0), net.spatial_size, sw_batch_size, eng, overlap=overlap,
+                                       mode=mode, return_labels=want_labels, return_logits=not want_labels)
     cropped_shape = tuple(hi[a] - lo[a] for a in range(3))
     if want_labels:
         lab = res["labels"][0, 0]
@@ -310,3 +316,77 @@ def predict(model_file: Path, test_images: List[Path], test_labels: Optional[Lis
         print("Total Conf. Matrix Metrics:")
         metrics = E.confusion_metrics(all_counts)
         print_table(list(E.CONFUSION_METRICS), [metrics[k] for k in E.CONFUSION_METRICS])
+
+
+
+def ensemble_creator(model_files: List[Path], test_images: List[Path], test_labels: Optional[List[Path]] = None,
+                     output_dir: Path = None, tissue_dict: Dict[str, int] = None, spacing: Sequence[float] = [],
+                     combination_mode: str = "select_best", candidate_per_tissue_path: Optional[Path] = None,
+                     gpu_ids: List[int] = [], *, precision: str = "fp32") -> None:
+    """Same signature as ``segmantic.seg.monai_unet.ensemble_creator`` (``:848-1004``): every model predicts every image
+    with ``SlidingWindowInferer(roi_size=(96, 96, 96), sw_batch_size=4, overlap=0.5)`` (``:834-846``; here the roi is the
+    models' own ``spatial_size``), the predictions are combined voxel-wise on the device and written as
+    ``<output_dir>/<image basename>_seg.nii.gz``.
+
+    * ``mean``: ``MeanEnsembled(weights=...)`` then argmax; the weights are parsed from the checkpoint names as the
+      reference does (``float(stem.split("-")[-1].split("=")[1])``, e.g. ``epoch=12-val_dice=0.91.ckpt``).
+    * ``vote``: argmax per model, majority vote (ties -> lowest class).
+    * ``select_best``: argmax per model; ``candidate_per_tissue_path`` (yaml / json ``{tissue name: model index}``)
+      picks, per tissue, the model whose voxels of that tissue are kept (``seg/transforms.py:15-61``).
+
+    Deviation: with ``spacing`` the combined LABEL map is resampled back nearest-neighbour; the reference runs
+    ``Invertd(nearest_interp=False)`` -- trilinear interpolation of label values -- on it."""
+    from ..image import nifti
+    from . import ensemble as ENS
+
+    mode_name = getattr(combination_mode, "value", combination_mode)
+    if mode_name not in ("mean", "vote", "select_best"):
+        raise ValueError(f"unknown combination mode {combination_mode!r}")
+    if mode_name == "select_best" and candidate_per_tissue_path is None:
+        raise ValueError("When using the 'select_best'-mode, candidate_per_tissue_path needs to be specified.")
+    device = make_device(gpu_ids)
+    if device.type != "cuda":
+        raise RuntimeError("segmantic_b200 has no CPU path: pass gpu_ids=[] or a non-negative GPU id")
+    model_files = [Path(f) for f in model_files]
+    if not model_files:
+        raise ValueError("ensemble_creator needs at least one model file")
+    models = []
+    for f in model_files:
+        settings = {}
+        if f.with_suffix(".json").exists():
+            settings = json.loads(f.with_suffix(".json").read_text())
+        m = Net.load_from_checkpoint(str(f), **settings)
+        m.freeze()
+        m.eval()
+        m.to(device)
+        models.append(m)
+    num_classes = models[0].num_classes
+    spec = {"nets": models, "mode": mode_name, "num_classes": num_classes}
+    if mode_name == "mean":
+        spec["weights"] = [float(f.stem.split("-")[-1].split("=")[1]) for f in model_files]
+    elif mode_name == "select_best":
+        if tissue_dict is None:
+            raise RuntimeError("'select_best' mode requires a tissue list")
+        text = Path(candidate_per_tissue_path).read_text()
+        if Path(candidate_per_tissue_path).suffix.lower() == ".json":
+            name_model = json.loads(text)
+        else:
+            import yaml
+            name_model = yaml.safe_load(text)
+        spec["pairs"] = [(int(tissue_dict[name]), int(model_id)) for name, model_id in name_model.items()]
+    if test_labels:
+        assert len(test_images) == len(test_labels)
+    if output_dir:
+        os.makedirs(output_dir, exist_ok=True)
+    for img_path in test_images:
+        img_path = Path(img_path)
+        image, affine, header = nifti.read(img_path)
+        lab = predict_volume(models[0], torch.from_numpy(image), affine, spacing, overlap=0.5, mode="constant",
+                             sw_batch_size=4, precision=precision, invert="labels", ensemble=spec)
+        if output_dir:
+            name = img_path.name
+            for ext in (".nii.gz", ".nii", ".nrrd", ".mha", ".mhd"):
+                if name.endswith(ext):
+                    name = name[: -len(ext)]
+                    break
+            nifti.write(Path(output_dir) / f"{name}_seg.nii.gz", lab.numpy().astype(np.float32), affine)

@@ -189,3 +189,14 @@ def test_evaluation_oracle_known_answers():
     m = oe.confusion_metrics([counts])
     assert m == {"sensitivity": 5 / 8, "specificity": 13 / 16, "precision": 5 / 8, "accuracy": 18 / 24}
     assert np.array_equal(oe.confusion_matrix(2, np.array([0, 1, 7]), np.array([1, 1, 0])), [[0, 0], [1, 1]])
+
+
+def test_ensemble_oracle_known_answers():
+    """MeanEnsemble(weights) / VoteEnsemble / SelectBestEnsemble on hand-checked inputs."""
+    from oracle import ensemble as oens
+    labs = torch.tensor([[0, 1, 2, 2, 1], [0, 2, 2, 1, 0], [1, 2, 0, 1, 3]])
+    assert oens.vote_ensemble(labs, 3).tolist() == [0, 2, 2, 1, 0]          # 1-1-1 tie / out-of-range label -> lowest class
+    assert oens.select_best_ensemble(labs, {1: 0, 2: 2}).tolist() == [0, 2, 0, 0, 1]  # later pairs overwrite, unclaimed -> 0
+    x = torch.tensor([[[1.0], [2.0]], [[3.0], [0.0]]])                        # [E=2, C=2, V=1]
+    assert torch.allclose(oens.mean_ensemble(x, [1.0, 3.0]), torch.tensor([[2.5], [0.5]]))  # w / mean(w) = 0.5, 1.5
+    assert torch.allclose(oens.mean_ensemble(x), torch.tensor([[2.0], [1.0]]))
