@@ -284,37 +284,44 @@ __global__ void __launch_bounds__(kRsThreads, 1) rs_conv_kernel(const RsArgs a, 
           // Input row r = i - 1 feeds output rows r-1 (k1 = 2), r (k1 = 1), r+1 (k1 = 0) = B rows [0,RP) [RP,2RP) [2RP,3RP);
           // the first / last two rows of the strip use the trailing / leading part of the same B tile.
           if (ni == 1) {
-            // Single issuer, straight-line form: head rows (-1, 0), uniform middle rows, tail rows (t1-1, t1); the
-            // only per-row work besides the three MMAs is two additions and two chunk tests.
+            // Single issuer (default).
 #define SGM_RS_MMA3(AROW, B0, ID, COL)                                                       \
   do {                                                                                       \
     tc_mma(tmem_base + (COL), d_hi | (AROW), d_hi | (B0), (ID), 1u);                         \
     tc_mma(tmem_base + (COL), d_hi | ((AROW) + 1u), d_hi | ((B0) + 2u * NB), (ID), 1u);      \
     tc_mma(tmem_base + (COL), d_hi | ((AROW) + 2u), d_hi | ((B0) + 4u * NB), (ID), 1u);      \
   } while (0)
-            if (!first) {
-              if (!rs_wait(CLR(0), vpar, a.error_flag, 44, abort_s)) { ok = false; break; }
-              tc_fence_after();
-            }
-            if (real) {
-              SGM_RS_MMA3(arow, wrot + 2u * RP, id3, 0u);
-              SGM_RS_MMA3(arow + W, wrot + (uint32_t)RP, id6, 0u);
-            }
-            arow += 2u * W;
-            uint32_t col = 0;
-            for (int i = 2; i < t1; ++i, arow += W, col += RP) {
-              if ((i & 3) == 0 && !first) {  // entering the chunk of output rows i .. i+3
-                if (!rs_wait(CLR(i >> 2), vpar, a.error_flag, 44, abort_s)) { ok = false; break; }
+            // chunk by chunk (four input rows = one "cleared" poll + one commit); interior chunks -- four uniform middle
+            // rows -- are straight-line code: 12 MMAs whose descriptors differ by constants
+            const int last_chunk = (H1 - 1) >> 2;
+            for (int c = 0; c <= last_chunk; ++c) {
+              const int i0 = 4 * c;
+              if (!first && i0 < t1) {  // entering the chunk of output rows i0 .. i0+3
+                if (!rs_wait(CLR(c), vpar, a.error_flag, 44, abort_s)) { ok = false; break; }
                 tc_fence_after();
               }
-              if (real) SGM_RS_MMA3(arow, wrot, id9, col);
-              if ((i & 3) == 3) tc_commit(FULL(i >> 2));
+              if (real) {
+                const uint32_t ar = arow + (uint32_t)i0 * W;
+                if (i0 >= 2 && i0 + 3 <= t1 - 1) {
+                  const uint32_t col = (uint32_t)(i0 - 2) * RP;
+                  SGM_RS_MMA3(ar, wrot, id9, col);
+                  SGM_RS_MMA3(ar + W, wrot, id9, col + RP);
+                  SGM_RS_MMA3(ar + 2u * W, wrot, id9, col + 2u * RP);
+                  SGM_RS_MMA3(ar + 3u * W, wrot, id9, col + 3u * RP);
+                } else {
+                  const int i1 = min(i0 + 4, H1);
+                  for (int i = i0; i < i1; ++i) {
+                    const int r = i - 1;
+                    const uint32_t col = (uint32_t)max(r - 1, 0) * RP;
+                    const uint32_t b0 = wrot + (r < 0 ? 2u * RP : (r == 0 ? (uint32_t)RP : 0u));
+                    const uint32_t id = (r < 0 || r == t1) ? id3 : ((r == 0 || r == t1 - 1) ? id6 : id9);
+                    SGM_RS_MMA3(arow + (uint32_t)i * W, b0, id, col);
+                  }
+                }
+              }
+              tc_commit(FULL(c));
             }
             if (!ok) break;
-            if (real) SGM_RS_MMA3(arow, wrot, id6, col);
-            if ((t1 & 3) == 3) tc_commit(FULL(t1 >> 2));
-            if (real) SGM_RS_MMA3(arow + W, wrot, id3, col + RP);
-            tc_commit(FULL((t1 + 1) >> 2));
 #undef SGM_RS_MMA3
           } else {
             int next_commit = 0;
