@@ -257,12 +257,26 @@ def sliding_window_inference(inputs: torch.Tensor, roi_size: Sequence[int], sw_b
     returned (axis 0 of the result covers ``[slab.x0, slab.x1)``).
     """
     net = predictor
-    if inputs.dim() != net.spatial_dims + 2 or inputs.shape[0] != 1:
+    # A 2-D network also takes a STACK of slices [1, Cin, Z, X, Y] (BASELINE configs[4]: slice-wise prediction): every
+    # slice is an independent 2-D image -- one schedule with roi (1, h, w) over (Z, X, Y), all slices' windows batched
+    # into the same network launches; results per slice are those of the 2-D call.
+    stack = net.spatial_dims == 2 and inputs.dim() == 5
+    if (inputs.dim() != net.spatial_dims + 2 and not stack) or inputs.shape[0] != 1:
         raise ValueError(f"inputs must be [1, Cin, *spatial], got {tuple(inputs.shape)}")
     if inputs.device != net.device or inputs.dtype != torch.float32:
         raise ValueError("inputs must be float32 on the predictor's CUDA device")
+    if stack and inputs.shape[2] > _lib.SGM_MAX_STARTS:  # the schedule holds at most SGM_MAX_STARTS starts per axis
+        if slab is not None:
+            raise ValueError("slab partitions of a slice stack are not supported: partition the stack itself")
+        parts = [sliding_window_inference(inputs[:, :, z:z + _lib.SGM_MAX_STARTS], roi_size, sw_batch_size, predictor,
+                                          overlap, mode, sigma_scale, return_labels=return_labels,
+                                          return_probs=return_probs, return_logits=return_logits)
+                 for z in range(0, inputs.shape[2], _lib.SGM_MAX_STARTS)]
+        if isinstance(parts[0], dict):
+            return {k: torch.cat([p_[k] for p_ in parts], dim=2) for k in parts[0]}
+        return torch.cat(parts, dim=2)
     spatial = tuple(inputs.shape[2:])
-    size3 = (1,) + spatial if net.spatial_dims == 2 else spatial
+    size3 = (1,) + spatial if (net.spatial_dims == 2 and not stack) else spatial
     roi3 = net.roi3(roi_size)
     sched = make_schedule(size3, roi3, overlap, mode, sigma_scale)
     vol = inputs[0].reshape((net.in_channels,) + size3)
@@ -308,7 +322,7 @@ def sliding_window_inference(inputs: torch.Tensor, roi_size: Sequence[int], sw_b
             else:
                 sl.append(slice(lo, lo + size3[a]))
         t = t[tuple(sl)]
-        if net.spatial_dims == 2:
+        if net.spatial_dims == 2 and not stack:
             t = t.squeeze(lead)
         return t.unsqueeze(0)
 

@@ -211,6 +211,35 @@ def predict_volume(net: Net, image: torch.Tensor, affine: Optional[np.ndarray] =
     return host
 
 
+def predict_stack_2d(net: Net, image: torch.Tensor, *, overlap: float = 0.25, mode: str = "constant",
+                     sw_batch_size: int = 4, precision: str = "fp32", normalize: bool = True,
+                     return_device: bool = False):
+    """Slice-wise prediction of a stack with a 2-D network (BASELINE configs[4]; the reference has no code for it --
+    SURVEY.md 8d defines the Z slices as independent 2-D images).  ``image``: ``[C, X, Y, Z]`` (ITK index order, any
+    device); z-score normalisation per channel over the whole stack (``NormalizeIntensityd`` on the loaded image), then
+    every slice ``[C, X, Y]`` goes through the 2-D sliding window; all slices' windows share the network launches.
+    Returns uint8 labels ``[X, Y, Z]``."""
+    if net.spatial_dims != 2:
+        raise ValueError("predict_stack_2d needs a network with spatial_dims=2")
+    if image.dim() != 4:
+        raise ValueError(f"image must be [C, X, Y, Z], got {tuple(image.shape)}")
+    eng = net.engine(precision)
+    img = image.to(eng.device, dtype=torch.float32, non_blocking=True)
+    if normalize:
+        img = T.normalize_intensity(img)
+    stack = img.permute(0, 3, 1, 2).contiguous()  # [C, Z, X, Y]
+    res = sliding_window_inference(stack.unsqueeze(0), net.spatial_size, sw_batch_size, eng, overlap=overlap, mode=mode,
+                                   return_labels=True, return_logits=False)
+    eng.check()
+    lab = res["labels"][0, 0].permute(1, 2, 0).contiguous()  # [X, Y, Z]
+    if return_device:
+        return lab
+    host = torch.empty(lab.shape, dtype=lab.dtype, pin_memory=True)
+    host.copy_(lab, non_blocking=True)
+    torch.cuda.current_stream(eng.device).synchronize()
+    return host
+
+
 def _nearest_back(lab: torch.Tensor, record) -> torch.Tensor:
     """Nearest-neighbour resample of a label map from the network grid back onto the pre-Spacing grid
     (ITK semantics, ``image/processing.resample_to_ref``)."""

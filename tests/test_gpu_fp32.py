@@ -161,3 +161,45 @@ def test_window_ownership_is_bit_identical(cuda_device, precision):
         labels = torch.cat([o["labels"] for o in outs], dim=0)
         assert torch.equal(logits, full["logits"][0]), f"world={world}"
         assert torch.equal(labels, full["labels"][0, 0]), f"world={world}"
+
+
+def test_slice_stack_with_2d_network_matches_per_slice_oracle(cuda_device):
+    """BASELINE configs[4] in small: a 2-channel 2-D UNet over a stack of slices.  The stack call (one schedule with
+    roi (1, h, w), all slices' windows batched) must equal the oracle's 2-D sliding window slice by slice, and the
+    device's own single-slice 2-D call bit for bit."""
+    eng = _engine()
+    onet, sd = make_oracle_net(2, 2, 4, seed=5)
+    stack = normalized_volume((6, 80, 72), seed=13, channels=2)       # [C, Z, X, Y]
+    roi = (48, 48)
+    net = eng.UNetB200(sd, spatial_dims=2, in_channels=2, out_channels=4, device=cuda_device, precision="fp32")
+    res = eng.sliding_window_inference(stack[None].to(cuda_device), roi, 4, net, overlap=0.25, mode="gaussian",
+                                       return_labels=True)
+    out = res["logits"].cpu()
+    assert out.shape == (1, 4, 6, 80, 72) and res["labels"].shape == (1, 1, 6, 80, 72)
+    for z in range(6):
+        sl = stack[:, z][None]
+        with torch.no_grad():
+            ref = osw.sliding_window_inference(sl, roi, 4, onet, overlap=0.25, mode="gaussian")
+        assert rel_err(out[:, :, z], ref) < FP32_TOL
+        one = eng.sliding_window_inference(sl.to(cuda_device), roi, 4, net, overlap=0.25, mode="gaussian")
+        assert torch.equal(one.cpu(), out[:, :, z])
+    assert torch.equal(res["labels"].cpu()[0, 0].long(), out[0].argmax(0))
+
+
+def test_predict_stack_2d(cuda_device):
+    from segmantic_b200.seg.monai_unet import Net, predict_stack_2d
+    onet, sd = make_oracle_net(2, 2, 4, seed=5)
+    net = Net(num_classes=4, num_channels=2, spatial_dims=2, spatial_size=[48, 48])
+    net.load_state_dict(sd)
+    net.to(cuda_device)
+    raw = normalized_volume((72, 64, 5), seed=17, channels=2) * 20.0 + 3.0   # [C, X, Y, Z]
+    lab = predict_stack_2d(net, raw)
+    assert lab.shape == (72, 64, 5) and lab.dtype == torch.uint8
+    norm = torch.stack([(raw[c] - raw[c].mean()) / raw[c].std(unbiased=False) for c in range(2)])
+    bad = 0
+    for z in range(5):
+        with torch.no_grad():
+            ref = osw.sliding_window_inference(norm[:, :, :, z][None], (48, 48), 4, onet)
+        b, _ = label_mismatch_outside_ties(ref[0], ref[0].argmax(0), lab[:, :, z].long(), 1e-3 * float(ref.abs().max()))
+        bad += b
+    assert bad == 0
