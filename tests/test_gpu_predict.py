@@ -94,3 +94,25 @@ def test_golden_forward_on_gpu(cuda_device):
     net1 = engine.UNetB200(sd1, spatial_dims=3, in_channels=1, out_channels=3, device=cuda_device, precision="fp32", **SMALL)
     sw = engine.sliding_window_inference(vol.to(cuda_device), (16, 16, 16), 4, net1, overlap=0.5, mode="gaussian").cpu().numpy()
     assert float(np.abs(sw - GOLD["sw_gauss"]).max() / np.abs(GOLD["sw_gauss"]).max()) < 1e-4
+
+
+def test_interpolate_to_reference_script(cuda_device, tmp_path):
+    """scripts/interpolate_to_reference.py (the reference's sitk_cli wrapper of resample_to_ref): a 1 mm label map back
+    onto an anisotropic reference grid, nearest neighbour -- bit-exact against the ITK oracle."""
+    from oracle import itk_resample as oitk
+    from segmantic_b200.image import nifti
+    rng = np.random.default_rng(3)
+    lab = rng.integers(0, 7, (40, 36, 51)).astype(np.float32)
+    aff_lab = osp.itk_geometry_to_ras_affine((1.0, 1.0, 1.0), (-20.0, -18.0, 0.0), np.eye(3).flatten())
+    aff_ref = osp.itk_geometry_to_ras_affine((0.5, 0.5, 3.0), (-20.0, -18.0, 0.0), np.eye(3).flatten())
+    nifti.write(tmp_path / "lab.nii.gz", lab, aff_lab)
+    nifti.write(tmp_path / "ref.nii.gz", np.zeros((80, 72, 17), np.float32), aff_ref)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "interpolate_to_reference.py"), "--moving-image",
+                          str(tmp_path / "lab.nii.gz"), "--fixed-image", str(tmp_path / "ref.nii.gz"), "--nearest",
+                          "--output", str(tmp_path / "out.nii.gz")], capture_output=True, text=True, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    res, aff, _ = nifti.read(tmp_path / "out.nii.gz")
+    assert res.shape == (1, 80, 72, 17) and np.allclose(aff, aff_ref)
+    expect = oitk.resample_to_ref(oitk.Image(lab.astype(np.uint8), (1.0, 1.0, 1.0), (-20.0, -18.0, 0.0)),
+                                  oitk.Image(np.zeros((80, 72, 17), np.uint8), (0.5, 0.5, 3.0), (-20.0, -18.0, 0.0)), True)
+    assert np.array_equal(res[0].astype(np.uint8), expect.array)
