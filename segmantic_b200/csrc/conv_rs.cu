@@ -113,7 +113,7 @@ __device__ __forceinline__ void rs_st_wait() { asm volatile("tcgen05.wait::st.sy
 // Bounded wait that fails soft: on a timeout (or when another role already gave up) the first wait code is kept in the
 // error flag, the CTA-wide abort flag is raised and the caller unwinds to the final barrier -- the kernel ends, and
 // sgm_unet_check reports the code instead of a dead context.
-constexpr long long kRsWaitCycles = 400000000LL;
+constexpr long long kRsWaitCycles = 2000000000LL;  // ~1 s: far beyond any legitimate wait, short enough to report instead of hanging
 __device__ __forceinline__ bool rs_wait(uint32_t bar, uint32_t parity, int* err, int code, volatile int* abort_s,
                                         unsigned sleep_ns = 0) {
   if (mbar_try_wait(bar, parity)) return true;
