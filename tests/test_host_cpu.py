@@ -225,3 +225,43 @@ def test_c_abi_exports_every_declared_symbol():
         handle = ctypes.c_void_p()
         rc = _lib.load().sgm_unet_create(ctypes.byref(desc), ctypes.byref(handle))
         assert rc == -2 and b"no CUDA device" in _lib.load().sgm_last_error()
+
+
+def test_ensemble_cli_and_argument_validation(tmp_path):
+    """`ensemble-predict` exposes the reference's options (commands/monai_unet_cli.py:212-246); ensemble_creator rejects what
+    the reference rejects (select_best without a candidate file, monai_unet.py:859-865) before touching a device."""
+    out = subprocess.run([sys.executable, "-m", "segmantic_b200.commands.monai_unet_cli", "ensemble-predict", "--help"],
+                         capture_output=True, text=True, cwd=ROOT)
+    assert out.returncode == 0, out.stderr
+    for opt in ("--datalist", "-d", "--models-dir", "-m", "--tissue-list", "-t", "--results-dir", "-r",
+                "--combination-mode", "-cm", "--candidate-yaml", "-cy", "--spacing", "--gpu-ids", "--datalist-key"):
+        assert opt in out.stdout, opt
+    from segmantic_b200.seg.monai_unet import ensemble_creator
+    with pytest.raises(ValueError):
+        ensemble_creator([tmp_path / "a.ckpt"], [], None, None, None, [], "select_best", None)
+    with pytest.raises(ValueError):
+        ensemble_creator([tmp_path / "a.ckpt"], [], None, None, None, [], "median", None)
+    with pytest.raises(RuntimeError):   # gpu_ids=[-1] is the reference's CPU switch: no CPU path here
+        ensemble_creator([tmp_path / "a.ckpt"], [], None, None, None, [], "vote", None, gpu_ids=[-1])
+
+
+def test_new_entry_points_fail_loudly_without_a_device():
+    """Evaluation / ensemble entry points: no CPU fallback (host wrappers raise, the C ABI returns SGM_ERR_CUDA)."""
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    from segmantic_b200 import _lib
+    from segmantic_b200.seg import ensemble as E
+    from segmantic_b200.seg import evaluation as EV
+    with pytest.raises(RuntimeError):
+        EV.confusion_matrix(3, np.zeros(8, np.uint8), np.zeros(8, np.uint8))
+    with pytest.raises(ValueError):
+        E.vote_ensemble(torch.zeros((2, 4), dtype=torch.uint8), 3)       # host tensor: not a CUDA tensor
+    lib = _lib.load()
+    buf = (ctypes.c_int64 * 16)()
+    rc = lib.sgm_confusion_matrix(ctypes.cast(buf, ctypes.c_void_p), ctypes.cast(buf, ctypes.c_void_p), 8, 3,
+                                  ctypes.cast(buf, ctypes.c_void_p), None, None)
+    assert rc == -2
+    # pure host arithmetic of the evaluation module needs no device
+    cm = np.array([[1, 1, 0], [0, 2, 1], [1, 0, 2]])
+    assert np.allclose(EV.class_dice(cm), [2 / 3, 2 / 3])
+    assert EV.confusion_metrics([EV.confusion_counts(cm)])["accuracy"] == 0.75
