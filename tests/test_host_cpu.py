@@ -265,3 +265,19 @@ def test_new_entry_points_fail_loudly_without_a_device():
     cm = np.array([[1, 1, 0], [0, 2, 1], [1, 0, 2]])
     assert np.allclose(EV.class_dice(cm), [2 / 3, 2 / 3])
     assert EV.confusion_metrics([EV.confusion_counts(cm)])["accuracy"] == 0.75
+
+
+def test_bench_reference_arm_json_contract():
+    """`bench.py --impl reference` (the CPU restatement timed on the host cores; needs no GPU): one JSON line with the
+    contract's keys, `impl: reference`, a cpu_baseline describing the run and an e2e object repeating the value."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--cpu-windows", "1"], capture_output=True, text=True, cwd=ROOT, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "Mvoxel/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert "workload" in line["config"]
