@@ -18,6 +18,11 @@ the published algorithms of those libraries, anchored on the reference's call si
                          ``CropForegroundd`` as configured at ``seg/monai_unet.py:151-176,612-625``
 * ``itk_resample.py``    ITK ``ResampleImageFilter`` as configured at ``image/processing.py:49-120``
 * ``predict.py``         the composition of the above = ``predict()`` at ``seg/monai_unet.py:551-670``
+* ``bf16_emulation.py``  the same UNet with the device path's bf16 rounding points (checks the tensor-core path)
+* ``evaluation.py``      ``confusion_matrix`` (``seg/evaluation.py:96-125``) and MONAI ``DiceMetric`` /
+                         ``ConfusionMatrixMetric`` as used at ``seg/monai_unet.py:640-725``
+* ``ensemble.py``        MONAI ``MeanEnsemble`` / ``VoteEnsemble`` and the reference's own ``SelectBestEnsemble``
+                         (``seg/transforms.py:15-61``) as used at ``seg/monai_unet.py:917-1003``
 
 The conv / grid_sample / argmax primitives underneath are the *real* ``torch`` CPU kernels (torch is
 installed), so layer-level arithmetic is executable-reference, only the composition is restated.
