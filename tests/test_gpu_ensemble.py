@@ -86,3 +86,21 @@ def test_ensemble_creator_end_to_end(cuda_device, tmp_path):
         assert float((got != expect[cm]).float().mean()) < 2e-3, cm
     with pytest.raises(ValueError):
         ensemble_creator(files, [tmp_path / "img.nii.gz"], None, tmp_path / "x", tissue, [], "select_best", None)
+
+
+def test_reference_fixtures_on_device(cuda_device):
+    """The reference's own golden vectors (tests/seg/test_transforms.py:8-27 SelectBestEnsembled, tests/seg/
+    test_evaluation.py:8-22 confusion matrix) through the device kernels."""
+    from segmantic_b200.seg import ensemble as E
+    from segmantic_b200.seg import evaluation as EV
+    preds = torch.stack([torch.ones(3, dtype=torch.uint8), torch.tensor([2, 0, 2], dtype=torch.uint8),
+                         torch.tensor([2, 1, 0], dtype=torch.uint8)]).to(cuda_device)
+    out = E.select_best_ensemble(preds, [(1, 0), (2, 1), (0, 2)])      # label_model_dict={1: 0, 2: 1, 0: 2}, in order
+    assert out.cpu().tolist() == [2, 1, 0]
+    field = np.zeros((10, 10), np.uint8)
+    field[2:3, 2:4] = 1
+    field[3:5, 3:4] = 2
+    view = field.T.flatten()
+    cm = EV.confusion_matrix(3, view, view)
+    assert np.all(np.diagonal(cm) == np.bincount(view))
+    assert np.all(np.diagonal(cm, offset=1) == 0) and np.all(np.diagonal(cm, offset=-1) == 0)

@@ -200,3 +200,22 @@ def test_ensemble_oracle_known_answers():
     x = torch.tensor([[[1.0], [2.0]], [[3.0], [0.0]]])                        # [E=2, C=2, V=1]
     assert torch.allclose(oens.mean_ensemble(x, [1.0, 3.0]), torch.tensor([[2.5], [0.5]]))  # w / mean(w) = 0.5, 1.5
     assert torch.allclose(oens.mean_ensemble(x), torch.tensor([[2.0], [1.0]]))
+
+
+def test_reference_fixtures_for_evaluation_and_ensemble():
+    """The reference's OWN golden vectors for these rows, replayed on the oracle:
+    tests/seg/test_evaluation.py:8-22 (confusion matrix of a 10x10 label field against itself: diagonal == bincount, zero
+    off-diagonals) and tests/seg/test_transforms.py:8-27 (SelectBestEnsembled on three label predictions)."""
+    from oracle import ensemble as oens
+    from oracle import evaluation as oe
+    field = np.zeros((10, 10), np.uint8)       # make_image(shape=(10, 10), value=0); sitk index [x, y]
+    field[2:3, 2:4] = 1
+    field[3:5, 3:4] = 2
+    view = field.T.flatten()                   # GetArrayViewFromImage: numpy order [y, x]
+    assert int(view.max()) + 1 == 3
+    cm = oe.confusion_matrix(3, view, view)
+    assert np.all(np.diagonal(cm) == np.bincount(view)) and list(np.bincount(view)) == [96, 2, 2]
+    assert np.all(np.diagonal(cm, offset=1) == 0) and np.all(np.diagonal(cm, offset=-1) == 0)
+    preds = torch.stack([torch.ones(3, dtype=torch.long), torch.tensor([2, 0, 2]), torch.tensor([2, 1, 0])])
+    out = oens.select_best_ensemble(preds, {1: 0, 2: 1, 0: 2})
+    assert out.tolist() == [2, 1, 0]
