@@ -49,3 +49,29 @@ def save_tissue_list(tissue_label_map: Dict[str, int], tissue_list_file_name: Pa
         for label in range(1, count + 1):
             g = label / max(count, 1)
             print(f"C{g:.2f} {1 - g:.2f} {0.5:.2f} {0.5:.2f} {by_label[label]}", file=f)
+
+
+def load_tissue_colors(file_name: Path) -> Dict[int, tuple]:
+    """``{label: (r, g, b)}`` from the ``C<r> <g> <b> <a> <name>`` lines of an iSEG tissue list (reference
+    ``image/labels.py:120-140``); label 0 (Background) is black."""
+    colors = {0: (0.0, 0.0, 0.0)}
+    with open(file_name) as f:
+        for raw in f:
+            if raw.startswith("C"):
+                r, g, b = (float(tok) for tok in raw[1:].split()[:3])
+                colors[len(colors)] = (r, g, b)
+    return colors
+
+
+def build_tissue_mapping(input_label_map: Dict[str, int], mapper):
+    """Merge / rename tissues (reference ``image/labels.py:13-37``): ``mapper`` maps a tissue name to its new name.
+    Returns the new ``{name: label}`` dict (Background first, the other names sorted) and the uint16 lookup table
+    ``old label -> new label`` to apply to a label field."""
+    import numpy as np
+
+    new_names = sorted({mapper(name) for name in input_label_map} - {"Background"})
+    output_label_map = {name: i for i, name in enumerate(["Background"] + new_names)}
+    lut = np.zeros(len(input_label_map), dtype=np.uint16)
+    for name, label in input_label_map.items():
+        lut[label] = output_label_map[mapper(name)]
+    return output_label_map, lut

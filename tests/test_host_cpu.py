@@ -281,3 +281,30 @@ def test_bench_reference_arm_json_contract():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
     assert "workload" in line["config"]
+
+
+def test_reference_label_fixtures(tmp_path):
+    """tests/image/test_labels.py of the reference replayed: tissue-list round trip (incl. colours) and tissue merging."""
+    from segmantic_b200.image import labels
+    tissue_map = {"Background": 0, "Bone": 1, "Fat": 2, "Skin": 3}
+    p = tmp_path / "tissue.txt"
+    labels.save_tissue_list(tissue_map, p)
+    assert labels.load_tissue_list(p) == tissue_map
+    assert len(labels.load_tissue_colors(p)) == len(tissue_map)
+
+    def _map_name(name):
+        return name if name in ("Background", "Bone") else "Other_tissue"
+
+    omap, i2o = labels.build_tissue_mapping(tissue_map, _map_name)
+    assert len(omap) == 3
+    assert omap == {_map_name(n1): i2o[i1] for n1, i1 in tissue_map.items()}
+    assert omap == {"Background": 0, "Bone": 1, "Other_tissue": 2} and i2o.tolist() == [0, 1, 2, 2]
+
+
+def test_reference_image_order_fixture():
+    """tests/image/test_image_order.py of the reference replayed: a view (no copy) with the axes reversed."""
+    from segmantic_b200.image.utils import array_view_reverse_ordering
+    im3d = np.random.default_rng(0).random((12, 13, 14))
+    im3d_f = array_view_reverse_ordering(im3d)
+    assert im3d_f.flags.owndata is False and im3d.shape == im3d_f.shape[::-1]
+    assert all(im3d[k, j, i] == im3d_f[i, j, k] for k in range(12) for j in range(13) for i in range(14))
