@@ -641,6 +641,7 @@ void tc_free(TcConv* c) {
   ps_free(c);
   pst_free(c);
   rs_free(c);
+  cs_free(c);
   if (c->w) cudaFree(c->w);
   if (c->bias) cudaFree(c->bias);
   delete c;
@@ -888,6 +889,13 @@ int tc_pack(const sgm_conv_desc* m, const sgm_conv_desc* second, int spatial_dim
     set_error("tc_pack: K-block descriptor bank exhausted / upload failed");
     tc_free(c);
     return SGM_ERR_CUDA;
+  }
+  {
+    int rc = cs_pack(m, second, c);
+    if (rc) {
+      tc_free(c);
+      return rc;
+    }
   }
   if (!second) {
     int rc = ps_pack(*m, c);
@@ -1156,6 +1164,7 @@ int tc_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t
   if (rs_applicable(c, io)) return rs_launch(c, io, error_flag_dev, st);
   if (ps_applicable(c, io)) return ps_launch(c, io, error_flag_dev, st);
   if (pst_applicable(c, io)) return pst_launch(c, io, error_flag_dev, st);
+  if (cs_applicable(c, io)) return cs_launch(c, io, error_flag_dev, st);
   const int key[8] = {io.id[0], io.id[1], io.id[2], io.od[0], io.od[1], io.od[2], io.n, io.cg0};
   auto* plans = reinterpret_cast<std::vector<PlanEntry>*>(c.plan_cache);
   const PlanEntry* pe = nullptr;

@@ -60,6 +60,9 @@ struct TcConv {
   __nv_bfloat16* rs_w = nullptr;   // device [3 rotations][3 k2][2][9*CP+16][8]
   int rs_cp = 0;                   // accumulator columns per (output row, plane slot); 0 = not eligible
   void* rs_plan_cache = nullptr;
+  // channel-streamed persistent packing (conv_cs.cu): K-heavy 3-D layers (>= 64 input channels; strided from 32)
+  __nv_bfloat16* cs_w = nullptr;   // device [coblk][16-channel chunk][tap block][2][NB][8]
+  void* cs_state = nullptr;        // CsState (packing geometry + launch plans); null = not eligible
 };
 
 struct TcIO {
@@ -107,6 +110,12 @@ int rs_pack(const sgm_conv_desc& d, TcConv* c);
 bool rs_applicable(const TcConv& c, const TcIO& io);
 int rs_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t st);
 void rs_free(TcConv* c);
+
+// channel-streamed persistent family (conv_cs.cu)
+int cs_pack(const sgm_conv_desc* main_desc, const sgm_conv_desc* second, TcConv* c);
+bool cs_applicable(const TcConv& c, const TcIO& io);
+int cs_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t st);
+void cs_free(TcConv* c);
 
 // transposed plane-sweep family (conv_pst.cu)
 int pst_pack(const sgm_conv_desc& d, TcConv* c);

@@ -16,7 +16,42 @@ def cg8(n, cg, dims, seed, dev, scale=1.0):
     return t.to(torch.bfloat16).to(dev)
 
 
-def run_case(net, name, idx, in0, in1=None, res=None, fused=False, cg_out2=0):
+def from_cg8(t, channels):
+    """CG8 [n, cg, d0, d1, d2, 8] -> NCDHW float32 [n, channels, d0, d1, d2]."""
+    n, cg = t.shape[:2]
+    return t.float().permute(0, 1, 5, 2, 3, 4).reshape(n, cg * 8, *t.shape[2:5])[:, :channels].contiguous()
+
+
+_FOLDED = {}
+
+
+def torch_conv_reference(idx, in0, in1=None, res=None, seed=0):
+    """The same layer through torch's own conv3d / conv_transpose3d (CPU, fp32) on the bf16 inputs with the
+    BN-folded, bf16-rounded weights: an independent statement of what the layer computes (not a repo kernel)."""
+    import torch.nn.functional as F
+    from segmantic_b200.seg.unet_spec import KIND_CONV_TRANSPOSE, fold_batchnorm, unet_conv_specs
+    if seed not in _FOLDED:
+        specs = unet_conv_specs(1, 10, (16, 32, 64, 128, 256), (2, 2, 2, 2))
+        _FOLDED[seed] = fold_batchnorm(synthetic_state_dict(3, 1, 10, seed=seed), specs)
+    f = _FOLDED[seed][idx]
+    sp = f.spec
+    x = from_cg8(in0.cpu(), in0.shape[1] * 8)
+    if in1 is not None:
+        x = torch.cat([x, from_cg8(in1.cpu(), in1.shape[1] * 8)], 1)
+    x = x[:, :sp.cin]
+    w = f.weight.to(torch.bfloat16).float()
+    if sp.kind == KIND_CONV_TRANSPOSE:
+        y = F.conv_transpose3d(x, w, f.bias, stride=sp.stride, padding=1, output_padding=sp.stride - 1)
+    else:
+        y = F.conv3d(x, w, f.bias, stride=sp.stride, padding=sp.kernel // 2)
+    if sp.has_adn:
+        y = torch.where(y > 0, y, y * f.alpha)
+    if res is not None:
+        y = y + from_cg8(res.cpu(), sp.cout)
+    return y
+
+
+def run_case(net, name, idx, in0, in1=None, res=None, fused=False, cg_out2=0, torch_check=False):
     try:
         print(f"START {name}", flush=True)
         ref = engine.debug_conv(net, idx, in0, in1, res, use_tc=False)
@@ -42,6 +77,19 @@ def run_case(net, name, idx, in0, in1=None, res=None, fused=False, cg_out2=0):
                 msg += f" firstbad={bad[0].tolist()} ref={float(r32[tuple(bad[0])]):.4g} got={float(o32[tuple(bad[0])]):.4g}"
                 msg += f" lastbad={bad[-1].tolist()} nz_out={int((o32 != 0).sum())}"
             print(("PASS " if good else "FAIL ") + msg, flush=True)
+        if torch_check:  # against torch's conv on the same bf16 inputs: <= one bf16 ulp of the output range
+            refs = [torch_conv_reference(idx, in0, in1, res)]
+            outs = [out]
+            if fused:
+                refs.append(torch_conv_reference(idx + 2, in0))
+                outs.append(out2)
+            for r, o in zip(refs, outs):
+                o32 = from_cg8(o.cpu(), r.shape[1])
+                scale = float(r.abs().max())
+                err = float((r - o32).abs().max())
+                good = err <= 1e-2 * max(scale, 1e-6)
+                ok &= good
+                print(("PASS " if good else "FAIL ") + f"{name:34s} torch max|ref|={scale:.4g} maxerr={err:.4g}", flush=True)
         return ok
     except Exception as e:  # noqa: BLE001
         print(f"ERROR {name}: {type(e).__name__}: {e}", flush=True)
@@ -110,6 +158,48 @@ def run(which="all"):
         results.append(run_case(net, "s2 64->128(+128) d3 fused 12^3", 9, cg8(1, 8, (12, 12, 12), 14, dev),
                                 fused=True, cg_out2=16))
         results.append(run_case(net, "s2 16->32 d1.unit0 alone 16^3", 3, cg8(1, 2, (16, 16, 16), 15, dev)))
+    if which in ("all", "cs"):
+        # channel-streamed persistent kernel (conv_cs.cu): several windows per unit (full and partial groups), units
+        # spread over the CTAs, residuals, ragged extents (sub-bricks), the two inputs of the transposed convs; every
+        # case also against torch's own conv3d / conv_transpose3d
+        results.append(run_case(net, "cs s1 64->64 d2.unit1 12^3 n3 +res", 7, cg8(3, 8, (12, 12, 12), 50, dev),
+                                res=cg8(3, 8, (12, 12, 12), 51, dev), torch_check=True))
+        results.append(run_case(net, "cs s1 128->128 d3.unit1 6^3 n5 +res", 10, cg8(5, 16, (6, 6, 6), 52, dev),
+                                res=cg8(5, 16, (6, 6, 6), 53, dev), torch_check=True))
+        results.append(run_case(net, "cs s1 128->256 bottom.unit0 6^3 n4", 12, cg8(4, 16, (6, 6, 6), 54, dev), torch_check=True))
+        results.append(run_case(net, "cs s1 256->256 bottom.unit1 6^3 n7", 13, cg8(7, 32, (6, 6, 6), 55, dev),
+                                res=cg8(7, 32, (6, 6, 6), 56, dev), torch_check=True))
+        results.append(run_case(net, "cs s1 256->256 bottom.unit1 6^3 n150", 13, cg8(150, 32, (6, 6, 6), 57, dev, 0.5),
+                                res=cg8(150, 32, (6, 6, 6), 58, dev)))
+        x = cg8(2, 8, (12, 12, 12), 59, dev)
+        results.append(run_case(net, "cs s1 64->64 up3.ru 12^3 n2 identity", 16, x, res=x, torch_check=True))
+        results.append(run_case(net, "cs s1 64->64 ragged 7x9x11 n2", 7, cg8(2, 8, (7, 9, 11), 60, dev), torch_check=True))
+        results.append(run_case(net, "cs s1 128->128 ragged 3x4x5 n9", 10, cg8(9, 16, (3, 4, 5), 61, dev), torch_check=True))
+        results.append(run_case(net, "cs s2 32->64(+64) d2 fused 24^3 n3", 6, cg8(3, 4, (24, 24, 24), 62, dev),
+                                fused=True, cg_out2=8, torch_check=True))
+        results.append(run_case(net, "cs s2 64->128(+128) d3 fused 12^3 n5", 9, cg8(5, 8, (12, 12, 12), 63, dev),
+                                fused=True, cg_out2=16, torch_check=True))
+        results.append(run_case(net, "cs s2 64->128(+128) ragged 10x6x14 n2", 9, cg8(2, 8, (10, 6, 14), 64, dev),
+                                fused=True, cg_out2=16, torch_check=True))
+        results.append(run_case(net, "cs t2 384->64 up3 6^3 n5", 15, cg8(5, 16, (6, 6, 6), 65, dev),
+                                cg8(5, 32, (6, 6, 6), 66, dev), torch_check=True))
+        results.append(run_case(net, "cs t2 128->32 up2 12^3 n3", 17, cg8(3, 8, (12, 12, 12), 67, dev),
+                                cg8(3, 8, (12, 12, 12), 68, dev), torch_check=True))
+        results.append(run_case(net, "cs t2 128->32 ragged 5x7x9 n2", 17, cg8(2, 8, (5, 7, 9), 69, dev),
+                                cg8(2, 8, (5, 7, 9), 70, dev), torch_check=True))
+    if which in ("all", "torch"):
+        # one direct torch comparison per remaining tcgen05 family (plane sweep, transposed plane sweep, brick kernel)
+        x = cg8(2, 2, (48, 48, 48), 80, dev)
+        results.append(run_case(net, "ps 16->16 up1.ru 48^3 n2 identity", 20, x, res=x, torch_check=True))
+        results.append(run_case(net, "ps 32->32 d1.unit1 24^3 global res", 4, cg8(1, 4, (24, 24, 24), 81, dev),
+                                res=cg8(1, 4, (24, 24, 24), 82, dev), torch_check=True))
+        results.append(run_case(net, "pst 64->16 up1 24^3 n2", 19, cg8(2, 4, (24, 24, 24), 83, dev),
+                                cg8(2, 4, (24, 24, 24), 84, dev), torch_check=True))
+        results.append(run_case(net, "pst 32->10 up0 48x32x40", 21, cg8(1, 2, (48, 32, 40), 85, dev),
+                                cg8(1, 2, (48, 32, 40), 86, dev), torch_check=True))
+        results.append(run_case(net, "brick s2 16->32(+32) d1 fused 48^3", 3, cg8(1, 2, (48, 48, 48), 87, dev),
+                                fused=True, cg_out2=4, torch_check=True))
+        results.append(run_case(net, "brick k1 128->256 bottom.residual 6^3", 14, cg8(2, 16, (6, 6, 6), 88, dev), torch_check=True))
     if which in ("all", "t2"):
         results.append(run_case(net, "t2 384->64 up3 6^3", 15, cg8(1, 16, (6, 6, 6), 16, dev), cg8(1, 32, (6, 6, 6), 17, dev)))
         results.append(run_case(net, "t2 128->32 up2 12^3", 17, cg8(1, 8, (12, 12, 12), 18, dev), cg8(1, 8, (12, 12, 12), 19, dev)))

@@ -1,12 +1,14 @@
 """Layer-level parity of the tcgen05 kernel families (generic brick kernel incl. channel-chunked deep layers,
 plane-sweep conv_ps, transposed plane-sweep conv_pst) against the CUDA-core kernels on identical bf16 CG8
-inputs: <= 2e-2 of the output range (one bf16 ulp of the largest value), through the C ABI (sgm_debug_conv)."""
+inputs: <= 2e-2 of the output range (one bf16 ulp of the largest value), through the C ABI (sgm_debug_conv).
+Groups "cs" (channel-streamed persistent kernel, conv_cs.cu) and "torch" additionally compare every case with torch's own
+conv3d / conv_transpose3d on the same bf16 inputs and BN-folded bf16 weights (<= 1e-2 of the output range)."""
 import pytest
 
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("group", ["s1", "ps", "s2", "t2"])
+@pytest.mark.parametrize("group", ["s1", "ps", "s2", "t2", "cs", "torch"])
 def test_tc_layers_match_cuda_core_kernels(cuda_device, group):
     from tests import diag_tc_layers
 
