@@ -232,6 +232,22 @@ SGM_API int32_t sgm_ensemble_select_best(const uint8_t* labels_in_dev, int32_t n
                                          const int32_t* tissue_ids, const int32_t* model_ids, int32_t n_pairs,
                                          uint8_t* labels_out_dev, void* stream);
 
+/* NVLink peer-memory exchange of the multi-GPU driver (one process per GPU; no counterpart in the reference, which
+ * predicts on gpu_ids[0] only: seg/utils.py:4-12 -- this is the data-parallel driver BASELINE.json's north_star adds).
+ * A rank exports a device buffer (any pointer inside a cudaMalloc allocation, e.g. a torch tensor of the default
+ * caching allocator) as a CUDA IPC handle; the neighbouring process maps it (sgm_p2p_open returns the BASE of the
+ * allocation, add `offset`), pushes data with the copy engines (sgm_p2p_put: cudaMemcpyAsync device-to-device over
+ * NVLink, no SM involved) and raises a 32-bit counter in the peer's memory (sgm_p2p_signal, ordered after everything
+ * queued before it on `stream`); the owner waits on its own stream until the counter reaches `value` (sgm_p2p_wait;
+ * after timeout_s seconds it gives up and sets *timeout_flag_dev = 1 instead of hanging the device). */
+SGM_API int32_t sgm_p2p_export(const void* ptr_dev, uint8_t handle[64], int64_t* offset);
+SGM_API int32_t sgm_p2p_open(const uint8_t handle[64], void** base_out);
+SGM_API int32_t sgm_p2p_close(void* base);
+SGM_API int32_t sgm_p2p_put(void* dst_peer_dev, const void* src_dev, int64_t bytes, void* stream);
+SGM_API int32_t sgm_p2p_signal(uint32_t* flag_peer_dev, uint32_t value, void* stream);
+SGM_API int32_t sgm_p2p_wait(const uint32_t* flag_dev, uint32_t value, int32_t* timeout_flag_dev, double timeout_s,
+                             void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -95,6 +95,12 @@ SIGNATURES = {
     "sgm_ensemble_vote": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     "sgm_ensemble_select_best": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                              C.c_int32, C.c_void_p, C.c_void_p]),
+    "sgm_p2p_export": (C.c_int32, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64)]),
+    "sgm_p2p_open": (C.c_int32, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "sgm_p2p_close": (C.c_int32, [C.c_void_p]),
+    "sgm_p2p_put": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "sgm_p2p_signal": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_void_p]),
+    "sgm_p2p_wait": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_double, C.c_void_p]),
     "sgm_confusion_matrix": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                          C.c_void_p]),
 }

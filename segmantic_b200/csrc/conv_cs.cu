@@ -34,12 +34,12 @@ namespace {
 using namespace tcptx;
 
 constexpr int kEpiWarps = 8;                      // two groups x the four TMEM lane quarters
-constexpr int kIssuers = 2;
+constexpr int kIssuers = 4;
 constexpr int kThreads = (kEpiWarps + 2 + kIssuers) * 32;   // + A producer + W producer
 constexpr int kSmemMax = 227 * 1024;
 constexpr int kMaxTaps = 32;
 constexpr int kMaxStages = 6;
-constexpr int kMaxTilesPerIssuer = 4;             // 512 TMEM columns / 64 columns per tile / 2 issuers
+constexpr int kMaxTilesPerIssuer = 2;             // 512 TMEM columns / 64 columns per tile / 4 issuers
 
 struct CsArgs {
   int mode;
@@ -83,6 +83,48 @@ __device__ __forceinline__ Unit decode_unit(const CsArgs& a, int u) {
   const int b01 = brick / a.nt[2];
   r.org[0] = (b01 / a.nt[1]) * a.t[0], r.org[1] = (b01 % a.nt[1]) * a.t[1], r.org[2] = b2 * a.t[2];
   return r;
+}
+
+struct IssueCtx {
+  uint32_t a_base16, w_base16, w_stage16, a_lbo, b_lbo, desc_hi, idesc, col_base, bar0;
+};
+
+// The K loop of one unit for an issuer that owns NMY row tiles (compile-time: no predicates around the MMAs).
+// Per 16-channel chunk: wait for the A stage; per weight stage: wait, then  taps x tiles  MMAs; commits release the
+// stages.  An issuer without tiles (NMY = 0) still waits and commits so that every barrier sees all its arrivals.
+template <int NMY>
+__device__ __forceinline__ void issue_unit(const CsArgs& a, const IssueCtx& ic, const uint32_t* tile_a, const uint32_t* tile_c,
+                                           int& sa, uint32_t& pa, int& sw, uint32_t& pw) {
+  const uint32_t NB2 = (uint32_t)(a.NB * 2);
+  uint32_t col[NMY > 0 ? NMY : 1];
+#pragma unroll
+  for (int q = 0; q < NMY; ++q) col[q] = ic.col_base + tile_c[q];
+  for (int kc = 0; kc < a.nkc; ++kc) {
+    mbar_wait_or_trap(ic.bar0 + 8u * sa, pa, a.error_flag, 54);  // AFULL(sa)
+    uint32_t a_tile[NMY > 0 ? NMY : 1];
+#pragma unroll
+    for (int q = 0; q < NMY; ++q) a_tile[q] = ((ic.a_base16 + (uint32_t)(sa * a.a_stage_units)) | ic.a_lbo) + tile_a[q];
+    int tap = 0;
+    for (int gi = 0; gi < a.ngw; ++gi) {
+      mbar_wait_or_trap(ic.bar0 + 8u * (2 * kMaxStages + sw), pw, a.error_flag, 55);  // WFULL(sw)
+      tc_fence_after();
+      uint32_t b_lo = (ic.w_base16 + (uint32_t)sw * ic.w_stage16) | ic.b_lbo;
+      const int nb = min(a.Gw, a.ntap - gi * a.Gw);
+#pragma unroll 3
+      for (int j = 0; j < nb; ++j, ++tap, b_lo += NB2) {
+        const uint32_t ta = a.tap_a[tap];
+        const uint32_t acc = (kc | tap) ? 1u : 0u;  // the very first MMA of a unit overwrites the accumulator
+        const uint64_t bdesc = ((uint64_t)ic.desc_hi << 32) | b_lo;
+#pragma unroll
+        for (int q = 0; q < NMY; ++q)
+          tc_mma(col[q], ((uint64_t)ic.desc_hi << 32) | (a_tile[q] + ta), bdesc, ic.idesc, acc);
+      }
+      tc_commit(ic.bar0 + 8u * (3 * kMaxStages + sw));  // WEMPTY(sw)
+      if (++sw == a.wstages) sw = 0, pw ^= 1u;
+    }
+    tc_commit(ic.bar0 + 8u * (kMaxStages + sa));  // AEMPTY(sa)
+    if (++sa == a.astages) sa = 0, pa ^= 1u;
+  }
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -231,31 +273,10 @@ cs_conv_kernel(const __grid_constant__ CsArgs a, const __grid_constant__ CUtenso
         if (use > 0) mbar_wait_or_trap(TEMPTY(buf), (uint32_t)(use - 1) & 1u, a.error_flag, 53);
         tc_fence_after();
         const uint32_t col_base = tmem_base + (uint32_t)(buf * 256);
-        for (int kc = 0; kc < a.nkc; ++kc) {
-          mbar_wait_or_trap(AFULL(sa), pa, a.error_flag, 54);
-          const uint32_t a_stage = (a_base16 + (uint32_t)(sa * a.a_stage_units)) | a_lbo;
-          int tap = 0;
-          for (int gi = 0; gi < a.ngw; ++gi) {
-            mbar_wait_or_trap(WFULL(sw), pw, a.error_flag, 55);
-            tc_fence_after();
-            uint32_t b_lo = (w_base16 + (uint32_t)sw * w_stage16) | b_lbo;
-            const int nb = min(a.Gw, a.ntap - gi * a.Gw);
-            for (int j = 0; j < nb; ++j, ++tap, b_lo += (uint32_t)(NB * 2)) {
-              const uint32_t ta = a.tap_a[tap], tcw = a.tap_c[tap];
-              const uint32_t acc = (kc == 0 && (tcw >> 31)) ? 0u : 1u;
-              const uint64_t bdesc = ((uint64_t)desc_hi << 32) | b_lo;
-              const uint32_t a_tap = a_stage + ta;
-              const uint32_t c_tap = col_base + (tcw & 0xffffu);
-#pragma unroll
-              for (int q = 0; q < kMaxTilesPerIssuer; ++q)
-                if (q < nmy) tc_mma(c_tap + tile_c[q], ((uint64_t)desc_hi << 32) | (a_tap + tile_a[q]), bdesc, idesc, acc);
-            }
-            tc_commit(WEMPTY(sw));
-            if (++sw == a.wstages) sw = 0, pw ^= 1u;
-          }
-          tc_commit(AEMPTY(sa));
-          if (++sa == a.astages) sa = 0, pa ^= 1u;
-        }
+        IssueCtx ic{a_base16, w_base16, w_stage16, a_lbo, b_lbo, desc_hi, idesc, col_base, bar0};
+        if (nmy >= 2) issue_unit<2>(a, ic, tile_a, tile_c, sa, pa, sw, pw);
+        else if (nmy == 1) issue_unit<1>(a, ic, tile_a, tile_c, sa, pa, sw, pw);
+        else issue_unit<0>(a, ic, tile_a, tile_c, sa, pa, sw, pw);
         tc_commit(TFULL(buf));
         if (tr && iw == 0 && uit < 6) a.trace[1 + uit] = clock64();
       }
@@ -431,7 +452,7 @@ int cs_pack(const sgm_conv_desc* m, const sgm_conv_desc* second, TcConv* c) {
   auto* st = new CsState();
   CsPack& p = st->pack;
   p.nkc = c->cgin / 2;
-  static const int n_pref = getenv("SGM_CS_N") ? atoi(getenv("SGM_CS_N")) : 64;
+  static const int n_pref = getenv("SGM_CS_N") ? atoi(getenv("SGM_CS_N")) : 128;  // measured: N = 128 beats 64 on every layer with >= 128 outputs
   if (c->mode == MODE_T2) {
     // parity classes folded into the MMA N dimension: 8 classes x 16 output channels, one tap block per input shift
     p.N = 16, p.NB = 128;

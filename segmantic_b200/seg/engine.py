@@ -445,26 +445,62 @@ class OwnedWindows:
         return out
 
 
+def _seam_link(net: UNetB200, run: "OwnedWindows", key: tuple, rank: int, world_size: int, group):
+    """The rank's ``p2p.SeamLink`` for this geometry (built collectively on first use: every rank sees the same
+    sequence of geometries, so the handle exchange stays matched across ranks)."""
+    from .p2p import SeamLink
+
+    link = net.__dict__.get("_seam")
+    if link is None or link.key != key or link.recv_buf.data_ptr() != run.wl.data_ptr():
+        if link is not None:
+            link.close()
+        link = SeamLink(run.wl, rank, world_size, group=group)
+        link.key = key
+        net.__dict__["_seam"] = link
+    return link
+
+
 def sliding_window_inference_owned(vol_slab: torch.Tensor, global_size: Sequence[int], part: dict,
                                    roi_size: Sequence[int], sw_batch_size: int, predictor: UNetB200,
                                    overlap: float = 0.25, mode: str = "constant", sigma_scale: float = 0.125,
-                                   *, rank: int = 0, world_size: int = 1, group=None, return_logits: bool = False):
+                                   *, rank: int = 0, world_size: int = 1, group=None, return_logits: bool = False,
+                                   exchange: Optional[str] = None):
     """Multi-GPU form with window OWNERSHIP (``sliding_window.window_partition``): this rank computes the
-    importance-weighted logits of its own windows only, sends the tail that also covers the next rank's planes
-    over NVLink (NCCL point-to-point), receives the corresponding tail of the previous rank, and blends its output
-    planes ``[part.x0, part.x1)`` in MONAI's window order -- bit-identical to the single-device result, and no
-    window is computed twice.  ``vol_slab``: ``[Cin, part.vol_x1 - part.vol_x0, Y, Z]`` float32 on the device."""
+    importance-weighted logits of its own windows only, pushes the tail that also covers the next rank's planes
+    over NVLink, and blends its output planes ``[part.x0, part.x1)`` in MONAI's window order -- bit-identical to the
+    single-device result, and no window is computed twice.  ``vol_slab``: ``[Cin, part.vol_x1 - part.vol_x0, Y, Z]``
+    float32 on the device.
+
+    ``exchange="p2p"`` (default; ``SGM_SEAM`` overrides): peer-memory push with the copy engines and device-side
+    counters (``p2p.SeamLink``), no collective library on the data path.  ``exchange="nccl"``: one NCCL point-to-point
+    send / receive per seam."""
     import torch.distributed as dist
 
+    exchange = exchange or os.environ.get("SGM_SEAM", "p2p")
+    run = OwnedWindows(vol_slab, global_size, part, roi_size, sw_batch_size, predictor, overlap, mode, sigma_scale)
+    if exchange == "p2p" and world_size > 1:
+        key = (tuple(int(s) for s in global_size), tuple(int(r) for r in roi_size), float(overlap), str(mode),
+               int(world_size), int(rank), predictor.out_channels)
+        link = _seam_link(predictor, run, key, rank, world_size, group if not isinstance(group, (tuple, list)) else None)
+        link.begin()
+        run.compute_tail()       # the tail the next rank waits for goes first; it travels while the rest is computed
+        link.push(run.send_view)
+        run.compute_rest()
+        if run.recv_view.numel() > 0:
+            link.wait_data()
+        out = run.blend(return_logits)
+        if run.recv_view.numel() > 0:
+            link.ack()
+        predictor.last_launch_count_owned = run.launches
+        return out
     # `group` may be a pair of process groups: the seam between ranks s and s+1 then uses group[s % 2], so that a
     # rank's receive (seam rank-1) and send (seam rank) live on different NCCL communicators.  On ONE communicator
     # unbatched point-to-point operations are serialised in posting order, which chains the seams across the ranks.
     seam_group = (lambda s: group[s % 2]) if isinstance(group, (tuple, list)) else (lambda s: group)
-    run = OwnedWindows(vol_slab, global_size, part, roi_size, sw_batch_size, predictor, overlap, mode, sigma_scale)
     reqs = []
     if rank > 0 and run.recv_view.numel() > 0:
         reqs.append(dist.irecv(run.recv_view, src=rank - 1, group=seam_group(rank - 1)))
-    run.compute_tail()  # the tail the next rank waits for goes first; it travels while the rest is computed
+    run.compute_tail()
     if rank + 1 < world_size and run.send_view.numel() > 0:
         reqs.append(dist.isend(run.send_view, dst=rank + 1, group=seam_group(rank)))
     run.compute_rest()

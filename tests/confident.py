@@ -48,8 +48,8 @@ def tissue_phantom(shape: Sequence[int], n_classes: int, seed: int = 0, noise: f
         jit = (torch.rand(3, generator=g) - 0.5) * 0.08
         centre = (-0.36 + 0.72 * i + float(jit[0]), -0.34 + 0.68 * j + float(jit[1]),
                   (-0.72 + 1.44 * (k + 0.5) / nk) * 0.62 / 0.72 + float(jit[2]))
-        radii = (torch.rand(3, generator=g) * 0.06 + 0.22).tolist()
-        radii[2] = min(radii[2], 0.55 / nk)
+        radii = (torch.rand(3, generator=g) * 0.05 + 0.27).tolist()
+        radii[2] = min(radii[2], 0.6 / nk)
         inside = sum(((gr - ce) / ra) ** 2 for gr, ce, ra in zip(grid, centre, radii)) < 1.0
         inside &= body
         labels[inside] = c
@@ -60,7 +60,8 @@ def tissue_phantom(shape: Sequence[int], n_classes: int, seed: int = 0, noise: f
 
 
 def train_confident_state_dict(n_classes: int = 10, steps: int = 300, patch: int = 48, seed: int = 0,
-                               device: str | torch.device = "cpu", verbose: bool = False) -> Dict[str, torch.Tensor]:
+                               device: str | torch.device = "cpu", verbose: bool = False,
+                               label_smoothing: float = 0.0) -> Dict[str, torch.Tensor]:
     """Fit the oracle UNet to ``tissue_phantom`` and return its ``state_dict`` (MONAI keys, CPU tensors)."""
     device = torch.device(device)
     torch.manual_seed(seed)
@@ -81,7 +82,7 @@ def train_confident_state_dict(n_classes: int = 10, steps: int = 300, patch: int
         x, y = torch.stack(xs), torch.stack(ys)
         for pg in opt.param_groups:
             pg["lr"] = 2e-3 * 0.5 * (1.0 + math.cos(math.pi * step / steps))
-        loss = F.cross_entropy(net(x), y)
+        loss = F.cross_entropy(net(x), y, label_smoothing=label_smoothing)
         opt.zero_grad(set_to_none=True)
         loss.backward()
         opt.step()
