@@ -11,9 +11,11 @@ accumulation, normalise + argmax.  (No resampling stage in this config: spacing 
   e2e     the same through the public API `segmantic_b200.seg.monai_unet.predict_volume` with HOST
           buffers: pinned H2D of the raw volume, z-score normalisation, foreground crop, prediction,
           D2H of the uint8 label map -- all inside the timed region.
-  N > 1   weak scaling: the volume grows to (256*N) x 256 x 256, axis 0 is cut into N output slabs with
-          ROI halos, every rank predicts its slab (bit-identical to the single-GPU result) and the uint8
-          label slabs are gathered over NCCL to rank 0; time = max over ranks.
+  N > 1   weak scaling: the volume grows to (256*N) x 256 x 256; the window list is split evenly over the ranks
+          (window ownership: no window is computed twice), a rank pushes the weighted logits of its last windows
+          into the next rank's memory over NVLink (copy engines, peer mapping), every rank blends its own planes
+          (bit-identical to the single-GPU result) and the uint8 label slabs are gathered over NCCL to rank 0;
+          time = max over ranks.
 
 `--impl reference` times the CPU restatement of the reference path (oracle/; the reference's own
 MONAI/SimpleITK stack is not installable here) on the host cores for the same workload, on a bounded
@@ -281,12 +283,16 @@ def run_b200(args):
     raw, norm = make_block(seed=1)
     gshape = (VOL[0] * world, VOL[1], VOL[2])
     sched = make_schedule(gshape, ROI, OVERLAP, MODE)
-    # N > 1: output slabs with ROI halos (default: no data-path collective at all) or, with SGM_MGPU=owned, window
-    # ownership + one NVLink point-to-point exchange per seam (faster: 2292 vs 2166 Mvoxel/s at N = 2, 3877 at N = 4;
-    # opt-in because one of six back-to-back 2-GPU runs stalled inside NCCL on this pool)
-    owned = world > 1 and os.environ.get("SGM_MGPU", "slab") == "owned"
+    # N > 1: window OWNERSHIP (default): the window list is split evenly, no window is computed twice, and the
+    # importance-weighted logits of a rank's last windows are pushed into the next rank's memory over NVLink by the copy
+    # engines (seg/p2p.py: CUDA IPC mapping + device-side counters, no collective library on the data path).
+    # SGM_MGPU=owned-nccl: the same partition with NCCL point-to-point; SGM_MGPU=slab: output slabs with ROI halos (no
+    # exchange at all, one redundant window row per cut: efficiency bound 5/6 .. 5/7).
+    mgpu = os.environ.get("SGM_MGPU", "owned")
+    owned = world > 1 and mgpu.startswith("owned")
+    exchange = "nccl" if mgpu == "owned-nccl" else "p2p"
     seam_groups = None
-    if owned:
+    if owned and exchange == "nccl":
         # two extra communicators: a rank's receive (from rank-1) and send (to rank+1) must not share one; their
         # pairwise NCCL communicators are created here, outside the timed steps
         seam_groups = (dist.new_group(), dist.new_group())
@@ -321,7 +327,8 @@ def run_b200(args):
             return res["labels"]
         if owned:  # every window once; the tail that covers the next rank's planes travels over NVLink
             res = engine.sliding_window_inference_owned(vol_dev, gshape, part, ROI, args.sw_batch, net, overlap=OVERLAP,
-                                                        mode=MODE, rank=rank, world_size=world, group=seam_groups)
+                                                        mode=MODE, rank=rank, world_size=world, group=seam_groups,
+                                                        exchange=exchange)
         else:
             res = engine.sliding_window_inference_slab(vol_dev, gshape, part, ROI, args.sw_batch, net, overlap=OVERLAP,
                                                        mode=MODE)
@@ -544,7 +551,8 @@ def run_b200(args):
                                      "gaussian blend, argmax labels",
                             windows=int(n_win if world == 1 else sched.n_windows),
                             sw_batch=max(args.sw_batch, int(os.environ.get("SGM_SW_BATCH", engine.DEVICE_SW_BATCH))),
-                            parallelism=(f"owned-windows{world}+p2p-halo" if owned else f"slab{world}") if world > 1 else "single",
+                            parallelism=(f"owned-windows{world}+{'nvlink-peer-push' if exchange == 'p2p' else 'nccl-p2p'}" if owned
+                                         else f"slab{world}") if world > 1 else "single",
                             l2="no flush: per-step working set (67 MB volume + 671 MB accumulator + activations) "
                                "exceeds the 126 MB L2"),
                 step_ms=dict(min=min(per_step), median=float(np.median(per_step)), max=max(per_step)),
@@ -559,6 +567,148 @@ def run_b200(args):
         dist.destroy_process_group()
     return 0
 
+
+# ------------------------------------------------------------------------- other BASELINE configs (not the headline)
+def _tiled_block(norm: torch.Tensor, x0: int, x1: int, shape):
+    """Planes [x0, x1) of the 256^3 block tiled periodically to `shape` ([1, x1 - x0, Y, Z] float32, host)."""
+    i0 = torch.arange(x0, x1) % norm.shape[1]
+    i1 = torch.arange(shape[1]) % norm.shape[2]
+    i2 = torch.arange(shape[2]) % norm.shape[3]
+    return norm[:, i0][:, :, i1][:, :, :, i2].contiguous()
+
+
+def run_config3(args):
+    """BASELINE configs[3]: whole-body 512 x 512 x 1024 volume, 20 tissues, STRONG scaling over N GPUs.  The 1024-voxel
+    axis is the slowest memory axis (axis 0 of the [X, Y, Z] tensor), so z-slabs are contiguous; N = 1 runs the window
+    list in chunks (the deferred-blend buffer of all 2100 windows is 148 GB), N > 1 splits it over the ranks (window
+    ownership + NVLink peer push) and gathers the uint8 label slabs on rank 0."""
+    import torch.distributed as dist
+    from segmantic_b200.seg import engine
+    from segmantic_b200.seg.multi_gpu import gather_label_slabs
+    from segmantic_b200.seg.sliding_window import make_schedule, window_partition
+    from segmantic_b200.synthetic import synthetic_state_dict
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    classes, gshape = 20, (1024, 512, 512)
+    sd = synthetic_state_dict(3, 1, classes, seed=0)
+    net = engine.UNetB200(sd, spatial_dims=3, in_channels=1, out_channels=classes, device=dev, precision=args.precision)
+    _, norm = make_block(seed=4)
+    sched = make_schedule(gshape, ROI, OVERLAP, MODE)
+    parts = window_partition(sched, world) if world > 1 else None
+    part = parts[rank] if parts else None
+    vol_dev = _tiled_block(norm, part["vol_x0"] if part else 0, part["vol_x1"] if part else gshape[0], gshape).to(dev)
+    n_win = (part["w_hi"] - part["w_lo"]) if part else sched.n_windows
+    log(f"[rank {rank}] configs[3]: volume {gshape}, {classes} tissues, {n_win} of {sched.n_windows} windows on this rank")
+
+    def step():
+        if part is None:
+            return engine.sliding_window_inference(vol_dev[None], ROI, args.sw_batch, net, overlap=OVERLAP, mode=MODE,
+                                                   return_labels=True, return_logits=False)["labels"]
+        res = engine.sliding_window_inference_owned(vol_dev, gshape, part, ROI, args.sw_batch, net, overlap=OVERLAP,
+                                                    mode=MODE, rank=rank, world_size=world)
+        return gather_label_slabs(res["labels"], parts, dst=0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    for _ in range(warm):
+        out = step()
+    net.check()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = step()
+    e1.record()
+    barrier()
+    net.check()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    checksum = int(out.to(torch.int64).sum().item()) if rank == 0 else 0
+    if rank == 0:
+        launches = getattr(net, "last_launch_count_owned", 0) if part else getattr(net, "last_launch_count_chunked", 0)
+        line = dict(metric=METRIC, value=float(np.prod(gshape)) / (ms * 1e-3) / 1e6, unit=UNIT, n_gpus=world, steps=steps,
+                    warmup=warm, ms_per_step=ms, higher_is_better=True, scaling="strong", vs_baseline=None,
+                    dtype=args.precision, data="synthetic",
+                    config=dict(workload="configs[3]: MONAI UNet3D, 20 tissues, synthetic whole-body 512x512x1024 volume "
+                                         "(the 1024 axis slowest), roi 96^3, overlap 0.5, gaussian blend, argmax labels",
+                                windows=int(sched.n_windows),
+                                parallelism=f"owned-windows{world}+nvlink-peer-push" if world > 1 else
+                                "single GPU, window list in chunks (deferred-blend buffer of 2100 windows = 148 GB)",
+                                l2="no flush: the working set is far larger than the 126 MB L2"),
+                    e2e=None, gpu_launches=int(launches * steps), label_checksum=checksum)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_config2(args):
+    """BASELINE configs[2]: the four-stage pipeline on an anisotropic 512 x 512 x 120 image at 0.5 x 0.5 x 3 mm --
+    trilinear Spacing to 1 mm isotropic (256 x 256 x 358), sliding-window prediction (10 tissues), argmax, nearest-
+    neighbour resample of the label map back onto the input grid -- through `predict_volume(..., spacing=(1, 1, 1),
+    invert="labels")`.  `value`: image resident on the device, labels left on the device; `e2e`: pinned host image in,
+    host label map out.  Mvoxel = voxels of the NETWORK-grid volume."""
+    from segmantic_b200.seg.monai_unet import Net, predict_volume
+    from segmantic_b200.synthetic import synthetic_state_dict, synthetic_volume
+
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(0)
+    sd = synthetic_state_dict(3, 1, CLASSES, seed=0)
+    pnet = Net(num_classes=CLASSES, num_channels=1, spatial_dims=3)
+    pnet.load_state_dict(sd)
+    pnet.to(dev)
+    src_shape, net_shape = (512, 512, 120), (256, 256, 358)
+    raw = synthetic_volume(src_shape, seed=2)
+    affine = np.diag([-0.5, -0.5, 3.0, 1.0])   # identity-direction ITK image (LPS) seen in RAS, 0.5 x 0.5 x 3 mm
+    host = raw.clone().pin_memory()
+    on_dev = raw.to(dev)
+    kw = dict(spacing=(1.0, 1.0, 1.0), overlap=OVERLAP, mode=MODE, sw_batch_size=args.sw_batch, precision=args.precision,
+              invert="labels", crop_foreground=False)
+    steps, warm = max(1, args.steps), max(3, args.warmup)
+    for _ in range(warm):
+        lab = predict_volume(pnet, on_dev, affine, return_device=True, **kw)
+    assert tuple(lab.shape) == src_shape
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        lab = predict_volume(pnet, on_dev, affine, return_device=True, **kw)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    for _ in range(2):
+        predict_volume(pnet, host, affine, **kw)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        hl = predict_volume(pnet, host, affine, **kw)
+    torch.cuda.synchronize(dev)
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / steps
+    nvox = float(np.prod(net_shape))
+    eng = pnet.engine(args.precision)
+    line = dict(metric=METRIC, value=nvox / (ms * 1e-3) / 1e6, unit=UNIT, n_gpus=1, steps=steps, warmup=warm, ms_per_step=ms,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype=args.precision, data="synthetic",
+                config=dict(workload="configs[2]: 512x512x120 @ 0.5x0.5x3 mm -> Spacing 1 mm (256x256x358) -> UNet3D 10 "
+                                     "tissues, roi 96^3, overlap 0.5, gaussian -> argmax -> nearest resample back to 512x512x120",
+                            stages="orientation, z-score, trilinear Spacing, sliding window + blend + argmax, ITK nearest back",
+                            l2="no flush: volumes and activations exceed the 126 MB L2"),
+                e2e=dict(value=nvox / (e2e_ms * 1e-3) / 1e6, unit=UNIT, ms_per_step=e2e_ms,
+                         h2d_bytes_per_step=int(host.numel() * 4), d2h_bytes_per_step=int(hl.numel())),
+                gpu_launches=int(eng.last_launch_count * steps), label_checksum=int(hl.to(torch.int64).sum().item()))
+    print(json.dumps(line), flush=True)
+    return 0
 
 
 def resample_rooflines(dev, pk, iters=12):
@@ -649,9 +799,16 @@ def main():
     ap.add_argument("--cpu-windows", type=int, default=32, help="windows in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3],
+                    help="BASELINE.json configs index: 1 = the headline (256^3, 10 tissues), 2 = the four-stage "
+                         "anisotropic pipeline, 3 = whole-body 512x512x1024 with 20 tissues (strong scaling)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.config == 3:
+        return run_config3(args)
+    if args.config == 2:
+        return run_config2(args)
     return run_b200(args)
 
 

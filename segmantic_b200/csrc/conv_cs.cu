@@ -443,11 +443,13 @@ int cs_pack(const sgm_conv_desc* m, const sgm_conv_desc* second, TcConv* c) {
   if (c->flat0 || m->kernel != 3 || !tma_available()) return SGM_OK;   // 3-D k3 convs only
   const int bit = c->mode == MODE_S1 ? 1 : (c->mode == MODE_S2 ? 2 : 4);
   if (!(cs_mask() & bit)) return SGM_OK;
-  // Which layers: K-heavy ones.  Layers with <= 32 input channels at stride 1 and the transposed convs with <= 16
-  // output channels stay on the plane-sweep kernels; the strided 16-channel block (down1) is bound by its input
-  // traffic, not by K, and keeps the brick kernel.
+  // Which layers: every strided block (>= 16 input channels), stride-1 convs with >= 64 input channels, transposed
+  // convs with >= 64.  Stride-1 layers with <= 32 channels and the transposed convs with <= 16 output channels stay on
+  // the plane-sweep kernels.  (The strided 16-channel block, K = 27 blocks only, is bound by the strided TMA loads of
+  // its parity slabs and by the epilogue: 0.65 -> 0.27 ms per 125 windows against the one-CTA-per-brick kernel.)
   if (c->mode == MODE_S1 && m->cin < 64) return SGM_OK;
-  if (c->mode == MODE_S2 && m->cin < 32) return SGM_OK;
+  static const int s2_min = getenv("SGM_CS_S2MIN") ? atoi(getenv("SGM_CS_S2MIN")) : 16;
+  if (c->mode == MODE_S2 && m->cin < s2_min) return SGM_OK;
   if (c->mode == MODE_T2 && (m->cin < 64 || c->ntot % 16 != 0)) return SGM_OK;
   auto* st = new CsState();
   CsPack& p = st->pack;

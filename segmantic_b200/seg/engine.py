@@ -225,6 +225,17 @@ def _sw_run(net: UNetB200, vol: torch.Tensor, sched: Schedule, sw_batch_size: in
                                           ws.data_ptr(), ws.numel(), st), "sgm_sw_predict")
         del keep
         return logits, labels, probs
+    full_call = (tuple(a0) == (0, len(sched.starts[0])) and tuple(vol_rng) == (0, sched.padded_size[0])
+                 and (x0, nx) == (0, sched.padded_size[0]))
+    if full_call and blend in ("auto", "chunked") and not return_probs:
+        # The deferred buffer of the whole volume does not fit (e.g. BASELINE configs[3] on ONE GPU: 2100 windows x 20
+        # classes x 96^3 x 4 B = 148 GB): run the window list in CHUNKS, each with its own deferred blend -- the
+        # window-ownership partition of the multi-GPU driver executed sequentially on one device (the "exchange" is a
+        # device copy of the seam windows).  Bit-identical to the one-shot form; no read-modify-write.
+        out = _sw_run_chunked(net, vol, sched, sw_batch_size, return_logits, return_labels, int(free_b * 0.8) + have)
+        if out is not None:
+            del keep
+            return out
     acc = torch.zeros((C_out, nx) + plane, dtype=torch.float32, device=net.device)
     with torch.cuda.device(net.device):
         need = lib.sgm_sw_workspace_bytes(net._handle, C.byref(cfg))
@@ -242,6 +253,51 @@ def _sw_run(net: UNetB200, vol: torch.Tensor, sched: Schedule, sw_batch_size: in
                    "sgm_sw_finalize")
     del keep
     return logits, labels, probs
+
+
+def _sw_run_chunked(net: UNetB200, vol: torch.Tensor, sched: Schedule, sw_batch_size: int, return_logits: bool,
+                    return_labels: bool, budget_bytes: int):
+    """Deferred blend in chunks of the window list (see ``_sw_run``); ``None`` when no chunking fits ``budget_bytes``."""
+    from .sliding_window import window_partition
+
+    roivox = int(sched.roi[0]) * int(sched.roi[1]) * int(sched.roi[2])
+    stride = net.out_channels * roivox * 4
+    device_batch = max(int(sw_batch_size), int(os.environ.get("SGM_SW_BATCH", DEVICE_SW_BATCH)))
+    with torch.cuda.device(net.device):
+        net_ws = int(net._lib.sgm_unet_workspace_bytes(net._handle, _lib.i3(sched.roi), min(device_batch, sched.n_windows)))
+    parts = None
+    for nchunks in range(2, len(sched.starts[0]) + 1):
+        try:
+            cand = window_partition(sched, nchunks)
+        except ValueError:
+            break
+        held = sorted((p["w_hi"] - p["wb"]) * stride for p in cand)
+        # two exchange buffers alternate (chunk r blends from buffer r % 2 while chunk r + 1's seam is copied in)
+        if held[-1] + (held[-2] if len(held) > 1 else 0) + net_ws + (256 << 20) <= budget_bytes:
+            parts = cand
+            break
+    if parts is None:
+        return None
+    size3 = sched.padded_size
+    logits, labels, launches = [], [], 0
+    prev = None
+    for r, part in enumerate(parts):
+        if part["w_hi"] <= part["w_lo"]:
+            continue
+        run = OwnedWindows(vol[:, part["vol_x0"]:part["vol_x1"]], size3, part, sched.roi, sw_batch_size, net,
+                           0.0, "constant", tag=f"chunk{r % 2}", sched=sched)  # (overlap / mode live in `sched`)
+        if prev is not None and run.recv_view.numel():
+            run.recv_view.copy_(prev.send_view)
+        run.compute_tail()
+        run.compute_rest()
+        out = run.blend(return_logits)
+        launches += run.launches
+        if return_logits:
+            logits.append(out["logits"])
+        labels.append(out["labels"])
+        prev = run
+    net.last_launch_count_chunked = launches
+    return (torch.cat(logits, dim=1) if return_logits else None, torch.cat(labels, dim=0) if return_labels else None, None)
 
 
 def sliding_window_inference(inputs: torch.Tensor, roi_size: Sequence[int], sw_batch_size: int,
@@ -371,9 +427,10 @@ class OwnedWindows:
 
     def __init__(self, vol_slab: torch.Tensor, global_size: Sequence[int], part: dict, roi_size: Sequence[int],
                  sw_batch_size: int, net: UNetB200, overlap: float, mode: str, sigma_scale: float = 0.125,
-                 tag: str = ""):
+                 tag: str = "", sched: Optional[Schedule] = None):
         size3 = tuple(int(s) for s in global_size)
-        sched = make_schedule(size3, net.roi3(roi_size), overlap, mode, sigma_scale)
+        if sched is None:
+            sched = make_schedule(size3, net.roi3(roi_size), overlap, mode, sigma_scale)
         if sched.padded_size != size3:
             raise ValueError("owned-window execution needs a volume at least as large as the roi along every axis")
         self.net, self.sched, self.part = net, sched, part

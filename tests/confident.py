@@ -64,6 +64,9 @@ def train_confident_state_dict(n_classes: int = 10, steps: int = 300, patch: int
                                label_smoothing: float = 0.0) -> Dict[str, torch.Tensor]:
     """Fit the oracle UNet to ``tissue_phantom`` and return its ``state_dict`` (MONAI keys, CPU tensors)."""
     device = torch.device(device)
+    # reproducible on a given GPU / library stack: deterministic cuDNN algorithms, fixed seeds (the parity tests do not
+    # depend on it -- both sides load the same weights -- but a pinned recipe keeps the tolerances' margins stable)
+    torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = True, False
     torch.manual_seed(seed)
     net = UNet(3, 1, n_classes).to(device)
     net.train()

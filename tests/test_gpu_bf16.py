@@ -155,3 +155,23 @@ def test_config2_full_size_properties(cuda_device, monkeypatch):
     assert torch.equal(g, r)
     # the two head kernels differ only in the fp32 summation order inside the conv: labels flip at near-ties only
     assert float((g != a).float().mean()) < 1e-4
+
+
+@pytest.mark.parametrize("cout,roi", [(10, (48, 48, 48)), (20, (32, 48, 32))])
+def test_chunked_deferred_blend_bit_identical(cuda_device, monkeypatch, cout, roi):
+    """Volumes whose deferred-blend buffer exceeds HBM (BASELINE configs[3] on one GPU: 148 GB) run the window list in
+    chunks -- the window-ownership partition executed sequentially on one device, the seam windows copied from chunk to
+    chunk.  Same head kernel, same fp32 additions in the same order: logits and labels equal the one-shot form bit for
+    bit (20 classes: the plane-sweep head and the generic transposed conv of the 11..32-class networks)."""
+    eng = _engine()
+    _, sd = make_oracle_net(3, 1, cout, seed=8)
+    vol = normalized_volume((176, 80, 96), seed=21)[None].to(cuda_device)
+    net = eng.UNetB200(sd, spatial_dims=3, in_channels=1, out_channels=cout, device=cuda_device, precision="bf16")
+    outs = {}
+    for mode in ("gather", "chunked"):
+        monkeypatch.setenv("SGM_BLEND", mode)
+        outs[mode] = eng.sliding_window_inference(vol, roi, 4, net, overlap=0.5, mode="gaussian", return_labels=True)
+        net.check()
+    assert getattr(net, "last_launch_count_chunked", 0) > 0   # the chunked path really ran
+    for k in ("logits", "labels"):
+        assert torch.equal(outs["gather"][k], outs["chunked"][k]), k
