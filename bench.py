@@ -261,7 +261,7 @@ def run_reference(args):
 def run_b200(args):
     import torch.distributed as dist
     from segmantic_b200.seg import engine
-    from segmantic_b200.seg.monai_unet import Net, predict_volume
+    from segmantic_b200.seg.monai_unet import Net, predict_volume, predict_volumes
     from segmantic_b200.seg.multi_gpu import gather_label_slabs
     from segmantic_b200.seg.sliding_window import make_schedule, slab_partition, window_partition
     from segmantic_b200.seg.unet_spec import unet_conv_specs
@@ -429,10 +429,14 @@ def run_b200(args):
             barrier()
             t0 = time.perf_counter()
             calls = []
-            for _ in range(e2e_steps):
-                tc0 = time.perf_counter()
-                lab = predict_volume(pnet, host, None, (), **kw)  # returns a HOST uint8 label map
-                calls.append((time.perf_counter() - tc0) * 1e3)
+            # predict_volumes = the loop of predict() over its images: every volume is uploaded from the pinned host
+            # buffer and its label map downloaded inside this region; the copies of neighbouring volumes overlap the
+            # prediction of the current one (copy engines on their own streams)
+            tc0 = time.perf_counter()
+            for lab in predict_volumes(pnet, [host] * e2e_steps, None, (), **kw):  # HOST uint8 label maps, in order
+                tc1 = time.perf_counter()
+                calls.append((tc1 - tc0) * 1e3)
+                tc0 = tc1
             torch.cuda.synchronize(dev)
             e2e_regions.append(((time.perf_counter() - t0) * 1e3 / e2e_steps, calls))
             tt = torch.tensor([max(calls) / float(np.median(calls))], dtype=torch.float64, device=dev)
@@ -452,7 +456,10 @@ def run_b200(args):
                    ms_per_step=e2e_ms, ms_per_call=dict(min=min(e2e_calls), median=float(np.median(e2e_calls)),
                                                         max=max(e2e_calls)),
                    regions_ms=[round(r[0], 3) for r in e2e_regions],
-                   note="predict_volume(host fp32 volume) -> host uint8 labels; N>1: one 256^3 volume per rank")
+                   note="predict_volumes(K pinned host fp32 volumes) -> K host uint8 label maps (the loop of predict() over its "
+                        "images): every volume crosses PCIe once each way inside the timed region, the copies of "
+                        "neighbouring volumes overlap the prediction of the current one; ms_per_call = interval between "
+                        "yielded label maps; N>1: one 256^3 volume per rank and step")
 
     if rank != 0:
         if world > 1:
@@ -636,6 +643,16 @@ def run_config3(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     checksum = int(out.to(torch.int64).sum().item()) if rank == 0 else 0
+    layers = None
+    if not args.no_profile:   # one more step with a CUDA-event pair around every launch: where the time goes
+        net.set_profiling(True)
+        net.get_profile()
+        step()
+        barrier()
+        prof = net.get_profile()
+        net.set_profiling(False)
+        layers = [dict(conv=r, ms_per_step=round(m, 3), launches=c) for r, m, c in prof if c]
+        log(f"[rank {rank}] per-layer ms: " + ", ".join(f"{l['conv']} {l['ms_per_step']}" for l in layers))
     if rank == 0:
         launches = getattr(net, "last_launch_count_owned", 0) if part else getattr(net, "last_launch_count_chunked", 0)
         line = dict(metric=METRIC, value=float(np.prod(gshape)) / (ms * 1e-3) / 1e6, unit=UNIT, n_gpus=world, steps=steps,
@@ -647,7 +664,7 @@ def run_config3(args):
                                 parallelism=f"owned-windows{world}+nvlink-peer-push" if world > 1 else
                                 "single GPU, window list in chunks (deferred-blend buffer of 2100 windows = 148 GB)",
                                 l2="no flush: the working set is far larger than the 126 MB L2"),
-                    e2e=None, gpu_launches=int(launches * steps), label_checksum=checksum)
+                    e2e=None, gpu_launches=int(launches * steps), label_checksum=checksum, layers=layers)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -660,7 +677,7 @@ def run_config2(args):
     neighbour resample of the label map back onto the input grid -- through `predict_volume(..., spacing=(1, 1, 1),
     invert="labels")`.  `value`: image resident on the device, labels left on the device; `e2e`: pinned host image in,
     host label map out.  Mvoxel = voxels of the NETWORK-grid volume."""
-    from segmantic_b200.seg.monai_unet import Net, predict_volume
+    from segmantic_b200.seg.monai_unet import Net, predict_volume, predict_volumes
     from segmantic_b200.synthetic import synthetic_state_dict, synthetic_volume
 
     dev = torch.device("cuda:0")
@@ -692,8 +709,8 @@ def run_config2(args):
         predict_volume(pnet, host, affine, **kw)
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
-    for _ in range(steps):
-        hl = predict_volume(pnet, host, affine, **kw)
+    for hl in predict_volumes(pnet, [host] * steps, [affine] * steps, **kw):   # pipelined over the images, as predict()
+        pass
     torch.cuda.synchronize(dev)
     e2e_ms = (time.perf_counter() - t0) * 1e3 / steps
     nvox = float(np.prod(net_shape))

@@ -15,8 +15,6 @@ namespace sgm {
 
 namespace {
 
-constexpr int MAX_COVER = 8;
-
 struct FinalizeArgs {
   const float* acc;
   float* logits;
@@ -34,35 +32,42 @@ struct FinalizeArgs {
   float floor;
 };
 
-__device__ __forceinline__ int covering(const int* starts, int ns, int roi, int v, int* idx) {
-  int c = 0;
+// windows j in [lo, hi] cover v  (starts ascending: start[j] <= v < start[j] + roi); any number of them (overlap is
+// user-settable in [0, 1): at overlap 0.9 a voxel is covered by ten windows per axis)
+__device__ __forceinline__ void cover_range_g(const int* starts, int ns, int roi, int v, int& lo, int& hi) {
+  lo = ns, hi = -1;
   for (int j = 0; j < ns; ++j) {
     const int s = starts[j];
-    if (s <= v && v < s + roi && c < MAX_COVER) idx[c++] = v - s;
+    if (s <= v && v < s + roi) {
+      lo = min(lo, j);
+      hi = j;
+    }
   }
-  return c;
 }
 
 template <int CMAX>
 __global__ void __launch_bounds__(256) finalize_kernel(const FinalizeArgs a) {
   const long long vox = (long long)a.nx * a.d1 * a.d2;
   const long long stride = (long long)gridDim.x * blockDim.x;
+  const int* st0 = a.starts;
+  const int* st1 = a.starts + SGM_MAX_STARTS;
+  const int* st2 = a.starts + 2 * SGM_MAX_STARTS;
   for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < vox; v += stride) {
     const int z = (int)(v % a.d2);
     const long long t = v / a.d2;
     const int y = (int)(t % a.d1);
     const int x = (int)(t / a.d1) + a.x0;
-    int i0[MAX_COVER], i1[MAX_COVER], i2[MAX_COVER];
-    const int c0 = covering(a.starts, a.n_starts[0], a.roi[0], x, i0);
-    const int c1 = covering(a.starts + SGM_MAX_STARTS, a.n_starts[1], a.roi[1], y, i1);
-    const int c2 = covering(a.starts + 2 * SGM_MAX_STARTS, a.n_starts[2], a.roi[2], z, i2);
+    int p_lo, p_hi, q_lo, q_hi, r_lo, r_hi;
+    cover_range_g(st0, a.n_starts[0], a.roi[0], x, p_lo, p_hi);
+    cover_range_g(st1, a.n_starts[1], a.roi[1], y, q_lo, q_hi);
+    cover_range_g(st2, a.n_starts[2], a.roi[2], z, r_lo, r_hi);
     float count = 0.f;
-    for (int p = 0; p < c0; ++p) {
-      const float g0 = a.imap0[i0[p]];
-      for (int q = 0; q < c1; ++q) {
-        const float g01 = __fmul_rn(g0, a.imap1[i1[q]]);
-        for (int r = 0; r < c2; ++r)
-          count = __fadd_rn(count, fmaxf(__fmul_rn(g01, a.imap2[i2[r]]), a.floor));
+    for (int p = p_lo; p <= p_hi; ++p) {
+      const float g0 = a.imap0[x - st0[p]];
+      for (int q = q_lo; q <= q_hi; ++q) {
+        const float g01 = __fmul_rn(g0, a.imap1[y - st1[q]]);
+        for (int r = r_lo; r <= r_hi; ++r)
+          count = __fadd_rn(count, fmaxf(__fmul_rn(g01, a.imap2[z - st2[r]]), a.floor));
       }
     }
     float val[CMAX];
@@ -288,8 +293,23 @@ __global__ void __launch_bounds__(kGatherWarps * 32) gather_blend_cw_kernel(cons
 // larger by more than 2^-22 relative certainly has a larger quotient; anything closer (or tiny magnitudes, where the
 // quotient could underflow) is decided by the two exact divisions -- the labels are bit-identical to
 // `torch.argmax(acc / count)` while the common case does no division at all.
-template <int CT, bool FULL>
+template <int VEC> struct VecT;
+template <> struct VecT<4> { using F = float4; using U = uchar4; };
+template <> struct VecT<2> { using F = float2; using U = uchar2; };
+__device__ __forceinline__ void unpack_vec(const float4& v, float* x) { x[0] = v.x, x[1] = v.y, x[2] = v.z, x[3] = v.w; }
+__device__ __forceinline__ void unpack_vec(const float2& v, float* x) { x[0] = v.x, x[1] = v.y; }
+__device__ __forceinline__ void store_vec(float* p, const float* x, float4*) { __stcs(reinterpret_cast<float4*>(p), make_float4(x[0], x[1], x[2], x[3])); }
+__device__ __forceinline__ void store_vec(float* p, const float* x, float2*) { __stcs(reinterpret_cast<float2*>(p), make_float2(x[0], x[1])); }
+__device__ __forceinline__ void store_lab(uint8_t* p, const int* a, uchar4*) { *reinterpret_cast<uchar4*>(p) = make_uchar4((uint8_t)a[0], (uint8_t)a[1], (uint8_t)a[2], (uint8_t)a[3]); }
+__device__ __forceinline__ void store_lab(uint8_t* p, const int* a, uchar2*) { *reinterpret_cast<uchar2*>(p) = make_uchar2((uint8_t)a[0], (uint8_t)a[1]); }
+
+// VEC = 4 (or 2): consecutive axis-2 voxels per thread; needs dims[2], roi[2] and every axis-2 window start to be
+// multiples of VEC (aligned vector loads inside every covering window).  E.g. 256 x 256 x 358 (BASELINE configs[2]
+// after Spacing): the last axis-2 start is 358 - 96 = 262 -> VEC = 2.
+template <int CT, bool FULL, int VEC>
 __global__ void __launch_bounds__(128, 4) gather_blend_vt_kernel(const GatherArgs a) {
+  using F = typename VecT<VEC>::F;
+  using U = typename VecT<VEC>::U;
   __shared__ int s_st[3][SGM_MAX_STARTS];
   __shared__ float s_im[3][512];
   for (int i = threadIdx.x; i < 3 * SGM_MAX_STARTS; i += blockDim.x) s_st[i / SGM_MAX_STARTS][i % SGM_MAX_STARTS] = a.starts[i];
@@ -298,7 +318,7 @@ __global__ void __launch_bounds__(128, 4) gather_blend_vt_kernel(const GatherArg
   for (int i = threadIdx.x; i < a.roi[2]; i += blockDim.x) s_im[2][i] = a.imap2[i];
   __syncthreads();
   const int C = a.channels;
-  const int nq = a.d2 >> 2;  // voxel quads per row
+  const int nq = a.d2 / VEC;  // voxel groups per row
   const long long vox = (long long)a.nx * a.d1 * a.d2;
   const long long total = (long long)a.nx * a.d1 * nq;
   const long long step = (long long)gridDim.x * blockDim.x;
@@ -306,13 +326,15 @@ __global__ void __launch_bounds__(128, 4) gather_blend_vt_kernel(const GatherArg
     const int zq = (int)(i % nq);
     const long long row = i / nq;
     const int y = (int)(row % a.d1), xl = (int)(row / a.d1);
-    const int x = xl + a.x0, z = zq * 4;
+    const int x = xl + a.x0, z = zq * VEC;
     int p_lo, p_hi, q_lo, q_hi, r_lo, r_hi;
     cover_range(s_st[0], a.n_starts[0], a.roi[0], x, p_lo, p_hi);
     cover_range(s_st[1], a.n_starts[1], a.roi[1], y, q_lo, q_hi);
     cover_range(s_st[2], a.n_starts[2], a.roi[2], z, r_lo, r_hi);
     // ---- count map, MONAI's window order and roundings
-    float cnt[4] = {0.f, 0.f, 0.f, 0.f};
+    float cnt[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) cnt[k] = 0.f;
     for (int p = p_lo; p <= p_hi; ++p) {
       const float g0 = s_im[0][x - s_st[0][p]];
       for (int q = q_lo; q <= q_hi; ++q) {
@@ -320,19 +342,22 @@ __global__ void __launch_bounds__(128, 4) gather_blend_vt_kernel(const GatherArg
         for (int r = r_lo; r <= r_hi; ++r) {
           const float* g2 = &s_im[2][z - s_st[2][r]];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) cnt[k] = __fadd_rn(cnt[k], fmaxf(__fmul_rn(g01, g2[k]), a.floor));
+          for (int k = 0; k < VEC; ++k) cnt[k] = __fadd_rn(cnt[k], fmaxf(__fmul_rn(g01, g2[k]), a.floor));
         }
       }
     }
     const int pa = max(p_lo, a.a0_begin), pb = min(p_hi, a.a0_end - 1);  // windows of this rank
     const long long v = ((long long)xl * a.d1 + y) * a.d2 + z;
-    float best[4] = {0.f, 0.f, 0.f, 0.f};   // undivided sum of the current winner
-    float qbest[4] = {0.f, 0.f, 0.f, 0.f};  // logits mode: its quotient
-    int arg[4] = {0, 0, 0, 0};
-    for (int c0 = 0; c0 < C; c0 += CT) {
-      float acc[CT][4];
+    float best[VEC], qbest[VEC];   // undivided sum of the current winner; logits mode: its quotient
+    int arg[VEC];
 #pragma unroll
-      for (int c = 0; c < CT; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f;
+    for (int k = 0; k < VEC; ++k) best[k] = 0.f, qbest[k] = 0.f, arg[k] = 0;
+    for (int c0 = 0; c0 < C; c0 += CT) {
+      float acc[CT][VEC];
+#pragma unroll
+      for (int c = 0; c < CT; ++c)
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[c][k] = 0.f;
       const float* wl_c = a.wl + (long long)c0 * a.cstride + z;
       for (int p = pa; p <= pb; ++p) {
         const long long w0 = (long long)(p - a.a0_begin) * a.n_starts[1];
@@ -341,15 +366,17 @@ __global__ void __launch_bounds__(128, 4) gather_blend_vt_kernel(const GatherArg
           const float* src01 = wl_c + (w0 + q) * a.n_starts[2] * a.win_stride + (long long)(off0 + (y - s_st[1][q])) * a.roi[2];
           for (int r = r_lo; r <= r_hi; ++r) {
             const float* src = src01 + r * a.win_stride - s_st[2][r];
-            float4 t[CT];
+            F t[CT];
 #pragma unroll
             for (int c = 0; c < CT; ++c)
-              if (FULL || c0 + c < C) t[c] = __ldcs(reinterpret_cast<const float4*>(src + c * a.cstride));
+              if (FULL || c0 + c < C) t[c] = __ldcs(reinterpret_cast<const F*>(src + c * a.cstride));
 #pragma unroll
             for (int c = 0; c < CT; ++c)
               if (FULL || c0 + c < C) {
-                acc[c][0] = __fadd_rn(acc[c][0], t[c].x), acc[c][1] = __fadd_rn(acc[c][1], t[c].y);
-                acc[c][2] = __fadd_rn(acc[c][2], t[c].z), acc[c][3] = __fadd_rn(acc[c][3], t[c].w);
+                float tv[VEC];
+                unpack_vec(t[c], tv);
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) acc[c][k] = __fadd_rn(acc[c][k], tv[k]);
               }
           }
         }
@@ -358,20 +385,20 @@ __global__ void __launch_bounds__(128, 4) gather_blend_vt_kernel(const GatherArg
 #pragma unroll
         for (int c = 0; c < CT; ++c)
           if (FULL || c0 + c < C) {
-            float qv[4];
+            float qv[VEC];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < VEC; ++k) {
               qv[k] = __fdiv_rn(acc[c][k], cnt[k]);
               if (c0 + c == 0 || qv[k] > qbest[k]) qbest[k] = qv[k], arg[k] = c0 + c;
             }
-            __stcs(reinterpret_cast<float4*>(a.logits + (long long)(c0 + c) * vox + v), make_float4(qv[0], qv[1], qv[2], qv[3]));
+            store_vec(a.logits + (long long)(c0 + c) * vox + v, qv, (F*)nullptr);
           }
       } else {
 #pragma unroll
         for (int c = 0; c < CT; ++c)
           if (FULL || c0 + c < C) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < VEC; ++k) {
               const float s = acc[c][k], m = best[k];
               if (c0 + c == 0) {
                 best[k] = s;
@@ -384,21 +411,29 @@ __global__ void __launch_bounds__(128, 4) gather_blend_vt_kernel(const GatherArg
           }
       }
     }
-    if (a.labels)
-      *reinterpret_cast<uchar4*>(a.labels + v) = make_uchar4((uint8_t)arg[0], (uint8_t)arg[1], (uint8_t)arg[2], (uint8_t)arg[3]);
+    if (a.labels) store_lab(a.labels + v, arg, (U*)nullptr);
   }
 }
 
-template <int CT>
+template <int CT, int VEC>
 int launch_gather_vt(const GatherArgs& a, cudaStream_t st) {
-  const long long total = (long long)a.nx * a.d1 * (a.d2 >> 2);
+  const long long total = (long long)a.nx * a.d1 * (a.d2 / VEC);
   const int blocks = (int)std::max<long long>(1, std::min<long long>((total + 127) / 128, 148LL * 32));
   if (a.channels % CT == 0)
-    gather_blend_vt_kernel<CT, true><<<blocks, 128, 0, st>>>(a);
+    gather_blend_vt_kernel<CT, true, VEC><<<blocks, 128, 0, st>>>(a);
   else
-    gather_blend_vt_kernel<CT, false><<<blocks, 128, 0, st>>>(a);
+    gather_blend_vt_kernel<CT, false, VEC><<<blocks, 128, 0, st>>>(a);
   SGM_CUDA_CHECK(cudaGetLastError());
   return SGM_OK;
+}
+
+template <int VEC>
+int launch_gather_vt_c(const GatherArgs& a, int channels, cudaStream_t st) {
+  // classes per pass: a divisor of C keeps the unrolled class loops free of guards (no spills)
+  if (channels <= 4) return launch_gather_vt<4, VEC>(a, st);
+  if (channels % 10 == 0) return launch_gather_vt<10, VEC>(a, st);
+  if (channels <= 8 || channels % 8 == 0) return launch_gather_vt<8, VEC>(a, st);
+  return launch_gather_vt<10, VEC>(a, st);
 }
 
 }  // namespace
@@ -416,30 +451,28 @@ int launch_gather_blend(const float* wl, int channels, const sgm_sw_cfg* cfg, co
   a.starts = starts_dev;
   a.imap0 = imap_dev[0], a.imap1 = imap_dev[1], a.imap2 = imap_dev[2];
   a.floor = cfg->imap_floor;
-  bool vec4 = (a.d2 % 4 == 0) && (a.roi[2] % 4 == 0);
-  for (int j = 0; j < cfg->n_starts[2]; ++j) vec4 = vec4 && (cfg->starts[2][j] % 4 == 0);
+  auto aligned = [&](int m) {
+    bool ok = (a.d2 % m == 0) && (a.roi[2] % m == 0);
+    for (int j = 0; j < cfg->n_starts[2]; ++j) ok = ok && (cfg->starts[2][j] % m == 0);
+    return ok;
+  };
+  const bool vec4 = aligned(4), vec2 = aligned(2);
   if (channels > 64) {
     set_error("deferred blend supports at most 64 classes, got %d", channels);
     return SGM_ERR_UNSUPPORTED;
   }
   static const bool force_cw = getenv("SGM_BLEND_CW") != nullptr;  // A/B switch: the warp-per-class kernel
-  if (vec4 && !probs && !force_cw && std::max(a.roi[0], std::max(a.roi[1], a.roi[2])) <= 512) {
-    // classes per pass: a divisor of C keeps the unrolled class loops free of guards (no spills)
-    if (channels <= 4) return launch_gather_vt<4>(a, st);
-    if (channels % 10 == 0) return launch_gather_vt<10>(a, st);
-    if (channels <= 8 || channels % 8 == 0) return launch_gather_vt<8>(a, st);
-    return launch_gather_vt<10>(a, st);
-  }
+  if ((vec4 || vec2) && !probs && !force_cw && std::max(a.roi[0], std::max(a.roi[1], a.roi[2])) <= 512)
+    return vec4 ? launch_gather_vt_c<4>(a, channels, st) : launch_gather_vt_c<2>(a, channels, st);
   const int nwarps = std::min(channels, kGatherWarps);
   const long long nrows = (long long)a.nx * a.d1;
   const int blocks = (int)std::max<long long>(1, std::min<long long>(nrows, 148LL * 64));
   const size_t smem = ((size_t)2 * channels * 32 * (vec4 ? 4 : 1) + (size_t)a.d2 + 8) * sizeof(float);
   SGM_REQUIRE(smem <= 96 * 1024, SGM_ERR_UNSUPPORTED, "deferred blend: axis 2 of %d voxels does not fit shared memory", a.d2);
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr_once;
+  if (attr_once.first()) {
     SGM_CUDA_CHECK(cudaFuncSetAttribute(gather_blend_cw_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     SGM_CUDA_CHECK(cudaFuncSetAttribute(gather_blend_cw_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr = true;
   }
   if (vec4) {
     gather_blend_cw_kernel<4><<<blocks, nwarps * 32, smem, st>>>(a, nwarps);

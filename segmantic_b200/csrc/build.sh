@@ -8,6 +8,7 @@ FLAGS=(-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompil
        -Xcompiler -fvisibility=hidden)
 mkdir -p "$HERE/build"
 OBJS=()
+PIDS=()
 for src in "$HERE"/*.cu; do
   obj="$HERE/build/$(basename "${src%.cu}").o"
   stale=0
@@ -15,10 +16,14 @@ for src in "$HERE"/*.cu; do
     if [[ ! -f "$obj" || "$dep" -nt "$obj" ]]; then stale=1; fi
   done
   if [[ $stale == 1 ]]; then
+    rm -f "$obj"   # a failed compile must not leave a stale object for the link
     "$NVCC" "${FLAGS[@]}" ${SGM_PTXAS_V:+-Xptxas -v} -c "$src" -o "$obj" &
+    PIDS+=($!)
   fi
   OBJS+=("$obj")
 done
-wait
+for pid in "${PIDS[@]}"; do
+  wait "$pid" || { echo "build.sh: a compile failed" >&2; exit 1; }
+done
 "$NVCC" -shared -gencode arch=compute_100a,code=sm_100a -o "$OUT" "${OBJS[@]}"
 echo "built $OUT"

@@ -90,4 +90,28 @@ struct TcConvPlan;
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Process-wide lock for the library's few caches (tensor maps, K-block tables): handles are per device, but one
+// process may drive several devices from several threads (predict(gpu_ids=[0, 1, ...])).
+void lock_global();
+void unlock_global();
+struct GlobalLock {
+  GlobalLock() { lock_global(); }
+  ~GlobalLock() { unlock_global(); }
+};
+
+// One-time set-up per DEVICE at a call site (cudaFuncSetAttribute and __constant__ uploads apply to the current device
+// only):  static DeviceOnce once;  if (once.first()) { ... }
+struct DeviceOnce {
+  unsigned long long mask = 0;
+  bool first() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    GlobalLock g;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (mask & bit) return false;
+    mask |= bit;
+    return true;
+  }
+};
+
 }  // namespace sgm

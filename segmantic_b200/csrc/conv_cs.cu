@@ -685,10 +685,9 @@ int cs_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t
             a.mode, a.N, a.NB, a.ntap, a.nkc, a.ncoblk, a.rd[0], a.rd[1], a.rd[2], a.t[0], a.t[1], a.t[2], a.H[0], a.H[1],
             a.H[2], a.P, a.nslab, a.row_first, a.ntiles, a.G, a.nbuf, a.astages, a.a_stage_units * 16, a.wstages, a.Gw,
             a.w_stage_bytes, pe->smem_bytes, a.nunits, pe->grid);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.first()) {
     SGM_CUDA_CHECK(cudaFuncSetAttribute(cs_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-    attr_set = true;
   }
   static const bool trace_on = getenv("SGM_TRACE") != nullptr;
   static long long* trace_dev = nullptr;

@@ -524,10 +524,9 @@ int ps_plan(const TcConv& c, const TcIO& io, PsPlan& pl) {
 
 template <int CB, int NCGP, int OUTK>
 int launch_t(const PsArgs& a, const CUtensorMap& tm, int grid, int smem, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.first()) {
     SGM_CUDA_CHECK(cudaFuncSetAttribute(ps_conv_kernel<CB, NCGP, OUTK>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPsSmemMax));
-    attr_set = true;
   }
   ps_conv_kernel<CB, NCGP, OUTK><<<grid, ps_threads(CB), smem, st>>>(a, tm);
   SGM_CUDA_CHECK(cudaGetLastError());

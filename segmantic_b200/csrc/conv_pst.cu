@@ -41,7 +41,8 @@ struct PstArgs {
   uint32_t mH2;
   int nunits, units_per_win;
   int R;
-  int cg0, cg1, cgA, act;   // channel groups of the two inputs; output channel groups
+  int cg0, cg1, cgA, act;   // channel groups of the two inputs; output channel groups of the TENSOR (window stride)
+  int cg_first;             // first output channel group this launch writes (two groups = 16 channels per launch)
   float alpha;
   const __nv_bfloat16* w;
   const float* bias;
@@ -231,7 +232,7 @@ pst_conv_kernel(const PstArgs a, const __grid_constant__ CUtensorMap tmap0, cons
       const bool valid = q < a.H12 && h1 < a.t1 && h2 < a.t2 && r1 < a.D[1] && r2 < a.D[2];
       // output voxel of parity class (0, 0, 0); class (p0, p1, p2) adds (p0 * OD1 + p1) * OD2 + p2
       const long long obase = ((long long)(2 * x0) * OD1 + 2 * r1) * OD2 + 2 * r2;
-      __nv_bfloat16* dst0 = a.out + ((long long)n * a.cgA * ovox + obase) * 8;
+      __nv_bfloat16* dst0 = a.out + (((long long)n * a.cgA + a.cg_first) * ovox + obase) * 8;
       ok = mbar_wait(TFULL(egroup), (uint32_t)(T >> 2) & 1u, a.error_flag, 36);
       if (!ok) break;
       tc_fence_after();
@@ -258,7 +259,7 @@ pst_conv_kernel(const PstArgs a, const __grid_constant__ CUtensorMap tmap0, cons
             if (act) x = prelu(x, alpha), y = prelu(y, alpha);
             v0[c] = x, v1[c] = y;
           }
-          if (g < a.cgA) {  // 32 contiguous bytes: output voxels 2 r2 and 2 r2 + 1
+          if (a.cg_first + g < a.cgA) {  // 32 contiguous bytes: output voxels 2 r2 and 2 r2 + 1
             uint4* d = reinterpret_cast<uint4*>(dst + (long long)g * ovox * 8);
             d[0] = pack8(v0);
             d[1] = pack8(v1);
@@ -348,10 +349,9 @@ int pst_plan(const TcConv& c, const TcIO& io, PstPlan& pl) {
 
 template <int NCGP>
 int launch_t(const PstArgs& a, const CUtensorMap& tm0, const CUtensorMap& tm1, int grid, int smem, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.first()) {
     SGM_CUDA_CHECK(cudaFuncSetAttribute(pst_conv_kernel<NCGP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-    attr_set = true;
   }
   pst_conv_kernel<NCGP><<<grid, kThreads, smem, st>>>(a, tm0, tm1);
   SGM_CUDA_CHECK(cudaGetLastError());
@@ -364,11 +364,14 @@ int pst_pack(const sgm_conv_desc& d, TcConv* c) {
   c->pst_ncgp = 0;
   if (getenv("SGM_NO_PST")) return SGM_OK;
   if (d.kind != SGM_KIND_CONV_TRANSPOSE || d.kernel != 3 || d.stride != 2 || c->flat0 || c->mode != MODE_T2) return SGM_OK;
-  if (d.cout > 16 || d.cin % 16 != 0) return SGM_OK;
+  if (d.cout > 32 || d.cin % 16 != 0) return SGM_OK;   // 17..32 output channels (11..32 classes): two launches of 16
   const int ncgp = d.cin / 16;
   if (ncgp != 2 && ncgp != 4) return SGM_OK;  // instantiated: 32 and 64 input channels
   const int NKB = 8 * ncgp;
-  std::vector<uint16_t> w((size_t)NKB * 2 * kN * 8, 0);
+  const int npass = (d.cout + 15) / 16;
+  const size_t pass_elems = (size_t)NKB * 2 * kN * 8;
+  std::vector<uint16_t> w(pass_elems * npass, 0);
+  for (int pass = 0; pass < npass; ++pass)
   for (int s = 0; s < 8; ++s)
     for (int cp = 0; cp < ncgp; ++cp) {
       const int kb = s * ncgp + cp;
@@ -384,11 +387,12 @@ int pst_pack(const sgm_conv_desc& d, TcConv* c) {
         if (!used) continue;
         const int tap = (kk[0] * 3 + kk[1]) * 3 + kk[2];
         for (int kc = 0; kc < 2; ++kc)
-          for (int co = 0; co < d.cout; ++co)
+          for (int cl = 0; cl < 16 && pass * 16 + cl < d.cout; ++cl)
             for (int k8 = 0; k8 < 8; ++k8) {
-              const int ci = (cp * 2 + kc) * 8 + k8;
+              const int ci = (cp * 2 + kc) * 8 + k8, co = pass * 16 + cl;
               // ConvTranspose weight layout [Cin][Cout][27]
-              w[(((size_t)kb * 2 + kc) * kN + (cls * 16 + co)) * 8 + k8] = f2bf(d.weight[((size_t)ci * d.cout + co) * 27 + tap]);
+              w[pass * pass_elems + (((size_t)kb * 2 + kc) * kN + (cls * 16 + cl)) * 8 + k8] =
+                  f2bf(d.weight[((size_t)ci * d.cout + co) * 27 + tap]);
             }
       }
     }
@@ -398,6 +402,7 @@ int pst_pack(const sgm_conv_desc& d, TcConv* c) {
   }
   SGM_CUDA_CHECK(cudaMemcpy(c->pst_w, w.data(), w.size() * 2, cudaMemcpyHostToDevice));
   c->pst_ncgp = ncgp;
+  c->pst_npass = npass;
   c->pst_plan_cache = new std::vector<PstPlan>();
   return SGM_OK;
 }
@@ -459,9 +464,14 @@ int pst_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_
     rc = make_brick_map(&tm1, io.in1, io.n * io.cg1, io.id, box);
     if (rc) return rc;
   }
-  if (c.pst_ncgp == 2) rc = launch_t<2>(a, tm0, tm1, pe->grid, pe->smem_bytes, st);
-  else rc = launch_t<4>(a, tm0, tm1, pe->grid, pe->smem_bytes, st);
-  if (rc) return rc;
+  for (int pass = 0; pass < c.pst_npass; ++pass) {  // 16 output channels per launch
+    a.cg_first = 2 * pass;
+    a.w = c.pst_w + (size_t)pass * 8 * c.pst_ncgp * 2 * kN * 8;
+    a.bias = c.bias + 16 * pass;
+    if (c.pst_ncgp == 2) rc = launch_t<2>(a, tm0, tm1, pe->grid, pe->smem_bytes, st);
+    else rc = launch_t<4>(a, tm0, tm1, pe->grid, pe->smem_bytes, st);
+    if (rc) return rc;
+  }
   if (trace_on) {
     long long t[16];
     cudaStreamSynchronize(st);

@@ -663,10 +663,9 @@ int rs_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t
   rc = SGM_ERR_UNSUPPORTED;
 #define SGM_RS_CASE(CRV)                                                                                              \
   if (a.c_real == CRV) {                                                                                              \
-    static bool attr_set = false;                                                                                     \
-    if (!attr_set) {                                                                                                  \
+    static DeviceOnce attr_once;                                                                                      \
+    if (attr_once.first()) {                                                                                          \
       SGM_CUDA_CHECK(cudaFuncSetAttribute(rs_conv_kernel<10, CRV>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRsSmemMax)); \
-      attr_set = true;                                                                                                \
     }                                                                                                                 \
     rs_conv_kernel<10, CRV><<<pe->grid, kRsThreads, pe->smem_bytes, st>>>(a, tm);                                     \
     rc = SGM_OK;                                                                                                      \

@@ -653,10 +653,15 @@ struct BlkSlice {
   std::vector<uint32_t> words;
   int off;
 };
-static std::vector<BlkSlice> g_blk_slices;
-static int g_blk_used = 0;
+static std::vector<BlkSlice> g_blk_slices_dev[64];  // the __constant__ bank is per device
+static int g_blk_used_dev[64] = {0};
 
 static int blk_offset(const TcConv& c) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  GlobalLock lock;
+  std::vector<BlkSlice>& g_blk_slices = g_blk_slices_dev[dev & 63];
+  int& g_blk_used = g_blk_used_dev[dev & 63];
   std::vector<uint32_t> d(c.blocks.size());
   for (size_t i = 0; i < d.size(); ++i) {
     const KBlock& b = c.blocks[i];
@@ -944,6 +949,7 @@ struct MapEntry {
 static std::vector<MapEntry> g_maps;
 
 int make_brick_map(CUtensorMap* out, const void* ptr, int ncg, const int d[3], const int H[3], const int* par) {
+  GlobalLock lock;
   MapKey key{ptr, ncg, {d[0], d[1], d[2]}, {H[0], H[1], H[2]}, {par ? par[0] : 0, par ? par[1] : 0, par ? par[2] : 0}};
   for (auto& e : g_maps)
     if (memcmp(&e.key, &key, sizeof(key)) == 0) {
@@ -1213,12 +1219,11 @@ int tc_launch(const TcConv& c, const TcIO& io, int* error_flag_dev, cudaStream_t
             a.mode, N, nblk, a.ncls, a.cgin, a.rd[0], a.rd[1], a.rd[2], a.t[0], a.t[1], a.t[2], a.H[0], a.H[1], a.H[2],
             a.P, a.nslab, a.row_first, a.ntiles, a.tpc, a.nchunks, a.nbuf, a.cols_per_buf, a.tmem_cols, a.G, a.ngroups,
             a.nstages, a.resident, a.a_units, smem_bytes, a.use_tma, a.nt[0] * a.nt[1] * a.nt[2], c.ncoblk, io.n);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.first()) {
     SGM_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     SGM_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     SGM_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
   }
   static const bool trace_on = getenv("SGM_TRACE") != nullptr;
   static long long* trace_dev = nullptr;

@@ -54,6 +54,7 @@ struct TcConv {
   // output parity classes into the MMA N dimension
   __nv_bfloat16* pst_w = nullptr;  // device [8*ncgp][2][128][8], row n' = class*16 + co
   int pst_ncgp = 0;                // input channel pairs of groups (2 or 4); 0 = not eligible
+  int pst_npass = 1;               // launches of 16 output channels each (2 for 17..32 output channels)
   void* pst_plan_cache = nullptr;
   // row-sweep packing (conv_rs.cu): the head (<= 16 -> <= 10 channels, planar fp32 output) folds the d0 AND d1 taps
   // into the MMA N dimension through overlapping accumulator columns

@@ -515,11 +515,10 @@ static int launch_trilinear(const TriArgs& a, cudaStream_t st) {
   BrickPlan p;
   const long long ovox = (long long)a.od0 * a.od1 * a.od2;
   if (brick_plan(a, p)) {
-    static bool attr = false;
-    if (!attr) {
+    static DeviceOnce attr_once;
+    if (attr_once.first()) {
       SGM_CUDA_CHECK(cudaFuncSetAttribute(trilinear_brick_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
       SGM_CUDA_CHECK(cudaFuncSetAttribute(trilinear_brick_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
-      attr = true;
     }
     const long long ntiles = (long long)p.nt0 * p.nt1 * p.nt2;
     const size_t smem = (size_t)p.CC * p.S0 * p.S1 * p.S2 * sizeof(float);

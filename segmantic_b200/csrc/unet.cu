@@ -8,9 +8,14 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 namespace sgm {
+
+static std::recursive_mutex g_mutex;
+void lock_global() { g_mutex.lock(); }
+void unlock_global() { g_mutex.unlock(); }
 
 static thread_local char g_err[512] = "";
 
@@ -851,28 +856,32 @@ extern "C" int32_t sgm_sw_blend(const sgm_sw_cfg* cfg, int32_t channels, const f
   return launch_gather_blend(wl_dev, channels, cfg, starts_dev, imaps, logits_dev, labels_dev, probs_dev, st);
 }
 
-namespace {
-__constant__ int c_starts[3 * SGM_MAX_STARTS];
-__constant__ float c_imap[3 * 512];
-}  // namespace
-
 extern "C" int32_t sgm_sw_finalize(const float* acc_dev, int32_t channels, const sgm_sw_cfg* cfg,
                                    float* logits_dev, uint8_t* labels_dev, float* probs_dev, void* stream) {
   SGM_REQUIRE(acc_dev && channels >= 1, SGM_ERR_INVALID, "sgm_sw_finalize: bad argument");
   int rc = check_cfg(nullptr, cfg);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  SGM_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_starts, cfg->starts, sizeof(int) * 3 * SGM_MAX_STARTS, 0,
-                                         cudaMemcpyHostToDevice, st));
-  for (int a = 0; a < 3; ++a)
-    SGM_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_imap, cfg->imap[a], sizeof(float) * cfg->roi[a],
-                                           sizeof(float) * 512 * a, cudaMemcpyHostToDevice, st));
-  int* starts_ptr = nullptr;
-  float* imap_ptr = nullptr;
-  SGM_CUDA_CHECK(cudaGetSymbolAddress((void**)&starts_ptr, c_starts));
-  SGM_CUDA_CHECK(cudaGetSymbolAddress((void**)&imap_ptr, c_imap));
-  const float* imaps[3] = {imap_ptr, imap_ptr + 512, imap_ptr + 1024};
-  return launch_finalize(acc_dev, channels, cfg, starts_ptr, imaps, logits_dev, labels_dev, probs_dev, st);
+  // per-call tables from the stream-ordered allocator: concurrent finalisations (other networks / streams on the same
+  // device, different schedules) never share them
+  const size_t bytes = 3 * SGM_MAX_STARTS * sizeof(int) + 3 * 512 * sizeof(float);
+  char* tab = nullptr;
+  SGM_CUDA_CHECK(cudaMallocAsync((void**)&tab, bytes, st));
+  int* starts_ptr = (int*)tab;
+  float* imap_ptr = (float*)(tab + 3 * SGM_MAX_STARTS * sizeof(int));
+  cudaError_t e = cudaMemcpyAsync(starts_ptr, cfg->starts, sizeof(int) * 3 * SGM_MAX_STARTS, cudaMemcpyHostToDevice, st);
+  for (int a = 0; a < 3 && e == cudaSuccess; ++a)
+    e = cudaMemcpyAsync(imap_ptr + 512 * a, cfg->imap[a], sizeof(float) * cfg->roi[a], cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) {
+    const float* imaps[3] = {imap_ptr, imap_ptr + 512, imap_ptr + 1024};
+    rc = launch_finalize(acc_dev, channels, cfg, starts_ptr, imaps, logits_dev, labels_dev, probs_dev, st);
+  }
+  cudaFreeAsync(tab, st);
+  if (e != cudaSuccess) {
+    set_error("sgm_sw_finalize: table upload failed: %s", cudaGetErrorString(e));
+    return SGM_ERR_CUDA;
+  }
+  return rc;
 }
 
 extern "C" int32_t sgm_unet_check(sgm_unet* net, void* stream) {

@@ -232,7 +232,11 @@ def _sw_run(net: UNetB200, vol: torch.Tensor, sched: Schedule, sw_batch_size: in
         # classes x 96^3 x 4 B = 148 GB): run the window list in CHUNKS, each with its own deferred blend -- the
         # window-ownership partition of the multi-GPU driver executed sequentially on one device (the "exchange" is a
         # device copy of the seam windows).  Bit-identical to the one-shot form; no read-modify-write.
-        out = _sw_run_chunked(net, vol, sched, sw_batch_size, return_logits, return_labels, int(free_b * 0.8) + have)
+        # memory this call may use: what is free now plus what the network already holds from earlier calls (its
+        # workspace and the two chunk exchange buffers are cached on the engine and reused)
+        cached = sum(b.numel() * 4 for k_, b in net.__dict__.get("_bufs", {}).items() if k_.startswith("wlchunk") and b is not None)
+        out = _sw_run_chunked(net, vol, sched, sw_batch_size, return_logits, return_labels,
+                              int(free_b * 0.8) + have + cached)
         if out is not None:
             del keep
             return out

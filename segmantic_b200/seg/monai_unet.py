@@ -66,9 +66,19 @@ class Net:
     @classmethod
     def load_from_checkpoint(cls, checkpoint_path, map_location=None, **kwargs) -> "Net":
         """Lightning ``.ckpt`` or plain ``.pth``; ``kwargs`` override saved hyper-parameters."""
+        import pickle
+        import warnings
         try:
             ckpt = torch.load(str(checkpoint_path), map_location="cpu", weights_only=True)
-        except Exception:
+        except pickle.UnpicklingError as e:
+            # Lightning checkpoints may pickle objects the safe loader refuses (callbacks, omegaconf hyper-parameters).
+            # Full unpickling executes code from the file: only with the caller's explicit consent.  Missing / corrupt
+            # files (OSError, RuntimeError, EOFError) propagate unchanged.
+            if os.environ.get("SEGMANTIC_TRUST_CHECKPOINT", "0") != "1":
+                raise RuntimeError(
+                    f"{checkpoint_path} needs full unpickling ({e}); set SEGMANTIC_TRUST_CHECKPOINT=1 if you trust the "
+                    "file (torch.load(weights_only=False) can execute arbitrary code)") from e
+            warnings.warn(f"loading {checkpoint_path} with weights_only=False (SEGMANTIC_TRUST_CHECKPOINT=1)")
             ckpt = torch.load(str(checkpoint_path), map_location="cpu", weights_only=False)
         if isinstance(ckpt, dict) and "state_dict" in ckpt:
             hp = dict(ckpt.get("hyper_parameters", {}) or {})
@@ -122,12 +132,78 @@ def _infer_io_channels(sd, hp) -> dict:
     return out
 
 
+def predict_volumes(net: Net, images, affines=None, spacing: Sequence[float] = (), *, precision: str = "fp32",
+                    **kwargs):
+    """Pipelined ``predict_volume`` over a sequence of HOST images (the loop of ``predict()`` over ``test_images``,
+    ``monai_unet.py:663-670``): yields one host uint8 label map per image, in order.
+
+    The z-score normalisation needs the whole volume before the first window can run, so the upload of ONE volume
+    cannot overlap its own prediction; across volumes it can: the host->device copy of image ``i + 1`` (copy engine, its
+    own stream, second device buffer) and the device->host copy of label map ``i - 1`` run while the SMs predict image
+    ``i``.  Every image still crosses PCIe exactly once in each direction; results are those of ``predict_volume``."""
+    eng = net.engine(precision)
+    dev = eng.device
+    images = list(images)
+    affines = list(affines) if affines is not None else [None] * len(images)
+    if not images:
+        return
+    compute = torch.cuda.current_stream(dev)
+    copy_in, copy_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def upload(i):
+        src = images[i]
+        if src.device.type != "cpu":
+            return src, None
+        if not src.is_pinned():
+            src = src.pin_memory()
+        with torch.cuda.stream(copy_in):
+            d = src.to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_in)
+        return d, ev
+
+    pending = None          # (host label map, its copy event) of the previous image
+    nxt = upload(0)
+    for i in range(len(images)):
+        cur, ev = nxt
+        nxt = upload(i + 1) if i + 1 < len(images) else None   # queued BEFORE this image's kernels are launched
+        if ev is not None:
+            compute.wait_event(ev)
+        lab = predict_volume(net, cur, affines[i], spacing, precision=precision, return_device=True, check=False,
+                             **kwargs)
+        if ev is not None:
+            cur.record_stream(compute)
+        done = torch.cuda.Event()
+        done.record(compute)
+        host = torch.empty(lab.shape, dtype=lab.dtype, pin_memory=True)
+        with torch.cuda.stream(copy_out):
+            copy_out.wait_event(done)
+            host.copy_(lab, non_blocking=True)
+            lab.record_stream(copy_out)
+            out_ev = torch.cuda.Event()
+            out_ev.record(copy_out)
+        if pending is not None:
+            pending[1].synchronize()
+            yield pending[0]
+        pending = (host, out_ev)
+    pending[1].synchronize()
+    eng.check()   # a tcgen05 pipeline timeout anywhere in the sequence raises here
+    yield pending[0]
+
+
 def predict_volume(net: Net, image: torch.Tensor, affine: Optional[np.ndarray] = None,
                    spacing: Sequence[float] = (), *, overlap: float = 0.25, mode: str = "constant",
                    sw_batch_size: int = 4, precision: str = "fp32", invert: str = "logits",
                    normalize: bool = True, crop_foreground: bool = True, return_device: bool = False,
-                   ensemble: Optional[dict] = None):
+                   ensemble: Optional[dict] = None, check: bool = True, label: Optional[torch.Tensor] = None):
     """The array-level core of ``predict()`` (``monai_unet.py:589-670``) for ONE image.
+
+    ``label`` (``[X, Y, Z]``, the image's ground truth on the same grid): the evaluation branch of the reference --
+    ``default_preprocessing(keys=["image", "label"])`` (``monai_unet.py:151-176``) reorients the label with the image,
+    takes the foreground crop from ``label > 0`` instead of ``image > 0`` (``source_key="label"``, ``:167``) and sends
+    the label through the same ``Spacingd`` (bilinear, then ``.long()`` at ``:674``).  The call then returns
+    ``(label map on the original grid, prediction on the NETWORK grid, transformed label on the network grid)``, the
+    last two being what the reference scores (``:672-680``).
 
     ``image``: ``[C, X, Y, Z]`` (``[C, X, Y]`` for 2-D networks) in ITK index order, any device (host
     tensors are uploaded).  ``affine``: 4x4 RAS affine of that array (identity direction / unit spacing
@@ -152,7 +228,14 @@ def predict_volume(net: Net, image: torch.Tensor, affine: Optional[np.ndarray] =
         if nd == 3:
             affine[0, 0] = affine[1, 1] = -1.0  # identity-direction ITK image seen in RAS
     full_shape_itk = tuple(img.shape[1:])
+    lab_img = None
+    if label is not None:
+        if nd != 3:
+            raise ValueError("the labels-supplied evaluation branch is implemented for 3-D networks")
+        lab_img = label.to(dev, dtype=torch.float32, non_blocking=True).reshape((1,) + full_shape_itk)
     if nd == 3:
+        if lab_img is not None:
+            lab_img = T.orientation_ras(lab_img, affine)[0]
         img, aff, orient = T.orientation_ras(img, affine)
     else:
         aff, orient = np.asarray(affine, dtype=np.float64), None
@@ -161,9 +244,11 @@ def predict_volume(net: Net, image: torch.Tensor, affine: Optional[np.ndarray] =
     oriented_shape = tuple(img.shape[1:])
     lo, hi = [0, 0, 0], list(oriented_shape)
     if crop_foreground:
-        lo, hi = T.foreground_bbox(img)
+        lo, hi = T.foreground_bbox(lab_img if lab_img is not None else img)   # source_key = "label" when given
         if all(h > l for l, h in zip(lo, hi)):
             img = img[:, lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]].contiguous()
+            if lab_img is not None:
+                lab_img = lab_img[:, lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]].contiguous()
             shift = np.eye(4)
             shift[:3, 3] = lo
             aff = aff @ shift
@@ -171,16 +256,20 @@ def predict_volume(net: Net, image: torch.Tensor, affine: Optional[np.ndarray] =
             lo, hi = [0, 0, 0], list(oriented_shape)
     record = None
     if len(spacing) and nd == 3:
+        if lab_img is not None:
+            lab_img = T.spacing_forward(lab_img, aff, spacing)[0]
         img, aff, record = T.spacing_forward(img, aff, spacing)
     net_in = img if nd == 3 else img[:, 0]
     want_labels = record is None or invert == "labels" or ensemble is not None
+    want_net_labels = want_labels or lab_img is not None
     if ensemble is not None:
         # several models over the same pre-processed volume, combined on the network grid (ensemble_creator)
         from . import ensemble as ENS
         res = {"labels": ENS.combine(ensemble, net_in.unsqueeze(0), sw_batch_size, precision, overlap, mode)}
     else:
         res = sliding_window_inference(net_in.unsqueeze(0), net.spatial_size, sw_batch_size, eng, overlap=overlap,
-                                       mode=mode, return_labels=want_labels, return_logits=not want_labels)
+                                       mode=mode, return_labels=want_net_labels, return_logits=not want_labels)
+    pred_net = res["labels"][0, 0] if (lab_img is not None and isinstance(res, dict)) else None
     cropped_shape = tuple(hi[a] - lo[a] for a in range(3))
     if want_labels:
         lab = res["labels"][0, 0]
@@ -200,7 +289,12 @@ def predict_volume(net: Net, image: torch.Tensor, affine: Optional[np.ndarray] =
     assert tuple(lab.shape) == full_shape_itk
     if nd == 2:
         lab = lab[0]
-    eng.check()
+    if check:  # synchronises: the pipelined caller (predict_volumes) checks once at the end instead
+        eng.check()
+    if lab_img is not None:
+        # val_labels = test_data["label"].long() (monai_unet.py:674): truncation of the (bilinearly resampled) label
+        label_net = lab_img[0].to(torch.int64).clamp_(0, 255).to(torch.uint8)
+        return (lab if return_device else lab.cpu()), pred_net, label_net
     if return_device:
         return lab
     # device -> host into pinned memory (torch's caching host allocator reuses the block across calls; a pageable
@@ -301,37 +395,76 @@ def predict(model_file: Path, test_images: List[Path], test_labels: Optional[Lis
     class_dice_sum = np.zeros(max(num_classes - 1, 0))
     class_dice_cnt = np.zeros(max(num_classes - 1, 0))
     all_counts = []
-    for i, img_path in enumerate(test_images):
-        img_path = Path(img_path)
-        image, affine, header = nifti.read(img_path)  # [C, X, Y, Z] float32, RAS affine
-        lab_dev = predict_volume(net, torch.from_numpy(image), affine, spacing, overlap=overlap, mode=mode,
-                                 sw_batch_size=sw_batch_size, precision=precision, invert=invert, return_device=True)
+    # Several gpu_ids: the reference keeps gpu_ids[0] only (seg/utils.py:4-12).  Here the IMAGES of the call are spread
+    # round-robin over the listed devices (one worker thread and one engine per device; the C library releases the GIL),
+    # results are consumed in order.  One volume across several GPUs is the torchrun driver (seg/multi_gpu.py).
+    devices = [device]
+    if gpu_ids and len(gpu_ids) > 1:
+        devices = [torch.device(f"cuda:{int(g)}") for g in gpu_ids if int(g) >= 0] or [device]
+    import copy
+    nets = []
+    for d in devices:
+        nd_ = net if d == device else copy.copy(net)
+        if nd_ is not net:
+            nd_._engines = {}
+            nd_.to(d)
+        nets.append(nd_)
+
+    def run_one(i: int):
+        net_d = nets[i % len(nets)]
+        img_path = Path(test_images[i])
+        image, affine, _header = nifti.read(img_path)  # [C, X, Y, Z] float32, RAS affine
+        cm = None
+        with torch.cuda.device(net_d.device):
+            if have_labels:
+                ref_lab, _, _ = nifti.read(Path(test_labels[i]))
+                if tuple(ref_lab.shape[1:]) != tuple(image.shape[1:]):
+                    raise ValueError(f"label {test_labels[i]} has shape {tuple(ref_lab.shape[1:])}, image {tuple(image.shape[1:])}")
+                lab_dev, pred_net, label_net = predict_volume(
+                    net_d, torch.from_numpy(image), affine, spacing, overlap=overlap, mode=mode,
+                    sw_batch_size=sw_batch_size, precision=precision, invert=invert, return_device=True,
+                    label=torch.from_numpy(np.ascontiguousarray(ref_lab[0])))
+                # scored on the pre-processed (cropped, re-spaced) grid, before Invertd -- as the reference does (:672-680)
+                cm = E.confusion_matrix(num_classes, pred_net.contiguous(), label_net.contiguous())   # one device pass
+            else:
+                lab_dev = predict_volume(net_d, torch.from_numpy(image), affine, spacing, overlap=overlap, mode=mode,
+                                         sw_batch_size=sw_batch_size, precision=precision, invert=invert,
+                                         return_device=True)
+            lab_host = lab_dev.cpu().numpy().astype(np.float32)
+        return img_path, affine, lab_host, cm
+
+    if len(nets) > 1 and len(test_images) > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(max_workers=len(nets))
+        futures = [pool.submit(run_one, i) for i in range(len(test_images))]
+        results = (f.result() for f in futures)
+    else:
+        pool = None
+        results = (run_one(i) for i in range(len(test_images)))
+    for img_path, affine, lab_host, cm in results:
         name = img_path.name
         for ext in (".nii.gz", ".nii", ".nrrd", ".mha", ".mhd"):
             if name.endswith(ext):
                 name = name[: -len(ext)]
                 break
         if output_dir:
-            nifti.write(Path(output_dir) / f"{name}.nii.gz", lab_dev.cpu().numpy().astype(np.float32), affine)
+            nifti.write(Path(output_dir) / f"{name}.nii.gz", lab_host, affine)
         if have_labels:
-            ref_lab, _, _ = nifti.read(Path(test_labels[i]))
-            ref_dev = torch.from_numpy(np.ascontiguousarray(ref_lab[0])).to(lab_dev.device)
-            if tuple(ref_dev.shape) != tuple(lab_dev.shape):
-                raise ValueError(f"label {test_labels[i]} has shape {tuple(ref_dev.shape)}, prediction {tuple(lab_dev.shape)}")
-            cm = E.confusion_matrix(num_classes, lab_dev, ref_dev)   # one pass over both label maps on the device
             dice = E.class_dice(cm, include_background=False)
             valid = ~np.isnan(dice)
             class_dice_sum[valid] += dice[valid]
             class_dice_cnt[valid] += 1
             all_counts.append(E.confusion_counts(cm))
             image_mean_dice.append(float(np.nanmean(dice)) if valid.any() else float("nan"))
-            print("Mean Dice: ", image_mean_dice[-1])
+            print("Mean Dice: ", np.mean(dice))   # np.mean as the reference (:684): NaN when a tissue is absent from the label
             print("Class Dice:")
             print_table(tissue_names[1:], dice)
             all_mean_dice.append(float(np.nanmean(image_mean_dice)))
             if output_dir:
                 # the reference plots <base>_confusion.png (matplotlib, out of scope); the matrix itself is kept
                 np.savetxt(Path(output_dir) / f"{name}_confusion.csv", cm, fmt="%d", delimiter=",")
+    if pool is not None:
+        pool.shutdown()
     if output_dir is None:
         print("No output path specified, dice scores won't be saved.")
     else:

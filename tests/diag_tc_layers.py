@@ -25,15 +25,15 @@ def from_cg8(t, channels):
 _FOLDED = {}
 
 
-def torch_conv_reference(idx, in0, in1=None, res=None, seed=0):
+def torch_conv_reference(idx, in0, in1=None, res=None, seed=0, classes=10):
     """The same layer through torch's own conv3d / conv_transpose3d (CPU, fp32) on the bf16 inputs with the
     BN-folded, bf16-rounded weights: an independent statement of what the layer computes (not a repo kernel)."""
     import torch.nn.functional as F
     from segmantic_b200.seg.unet_spec import KIND_CONV_TRANSPOSE, fold_batchnorm, unet_conv_specs
-    if seed not in _FOLDED:
-        specs = unet_conv_specs(1, 10, (16, 32, 64, 128, 256), (2, 2, 2, 2))
-        _FOLDED[seed] = fold_batchnorm(synthetic_state_dict(3, 1, 10, seed=seed), specs)
-    f = _FOLDED[seed][idx]
+    if (seed, classes) not in _FOLDED:
+        specs = unet_conv_specs(1, classes, (16, 32, 64, 128, 256), (2, 2, 2, 2))
+        _FOLDED[(seed, classes)] = fold_batchnorm(synthetic_state_dict(3, 1, classes, seed=seed), specs)
+    f = _FOLDED[(seed, classes)][idx]
     sp = f.spec
     x = from_cg8(in0.cpu(), in0.shape[1] * 8)
     if in1 is not None:
@@ -51,7 +51,7 @@ def torch_conv_reference(idx, in0, in1=None, res=None, seed=0):
     return y
 
 
-def run_case(net, name, idx, in0, in1=None, res=None, fused=False, cg_out2=0, torch_check=False):
+def run_case(net, name, idx, in0, in1=None, res=None, fused=False, cg_out2=0, torch_check=False, classes=10):
     try:
         print(f"START {name}", flush=True)
         ref = engine.debug_conv(net, idx, in0, in1, res, use_tc=False)
@@ -78,7 +78,7 @@ def run_case(net, name, idx, in0, in1=None, res=None, fused=False, cg_out2=0, to
                 msg += f" lastbad={bad[-1].tolist()} nz_out={int((o32 != 0).sum())}"
             print(("PASS " if good else "FAIL ") + msg, flush=True)
         if torch_check:  # against torch's conv on the same bf16 inputs: <= one bf16 ulp of the output range
-            refs = [torch_conv_reference(idx, in0, in1, res)]
+            refs = [torch_conv_reference(idx, in0, in1, res, classes=classes)]
             outs = [out]
             if fused:
                 refs.append(torch_conv_reference(idx + 2, in0))
@@ -200,6 +200,15 @@ def run(which="all"):
         results.append(run_case(net, "brick s2 16->32(+32) d1 fused 48^3", 3, cg8(1, 2, (48, 48, 48), 87, dev),
                                 fused=True, cg_out2=4, torch_check=True))
         results.append(run_case(net, "brick k1 128->256 bottom.residual 6^3", 14, cg8(2, 16, (6, 6, 6), 88, dev), torch_check=True))
+    if which in ("all", "c20"):
+        # 20 tissues (BASELINE configs[3]): the transposed plane sweep in two launches of 16 output channels, the head
+        # on the plane-sweep kernel (11..32 classes)
+        sd20 = synthetic_state_dict(3, 1, 20, seed=0)
+        net20 = engine.UNetB200(sd20, spatial_dims=3, in_channels=1, out_channels=20, device=dev, precision="bf16")
+        results.append(run_case(net20, "pst 32->20 up0 24x32x40 n2 (two passes)", 21, cg8(2, 2, (24, 32, 40), 90, dev),
+                                cg8(2, 2, (24, 32, 40), 91, dev), torch_check=True, classes=20))
+        x = cg8(2, 4, (32, 48, 40), 92, dev)
+        results.append(run_case(net20, "ps 20->20 head 32x48x40 n2 identity", 22, x, res=x, torch_check=True, classes=20))
     if which in ("all", "t2"):
         results.append(run_case(net, "t2 384->64 up3 6^3", 15, cg8(1, 16, (6, 6, 6), 16, dev), cg8(1, 32, (6, 6, 6), 17, dev)))
         results.append(run_case(net, "t2 128->32 up2 12^3", 17, cg8(1, 8, (12, 12, 12), 18, dev), cg8(1, 8, (12, 12, 12), 19, dev)))

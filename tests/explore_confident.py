@@ -26,7 +26,7 @@ def digest(sd):
 dev = torch.device("cuda:0")
 vol, truth = tissue_phantom((256, 256, 256), 10, seed=11)
 x = vol[None]
-variants = [(3000, 0.1, 0), (3000, 0.1, 0), (3000, 0.1, 1), (2000, 0.1, 0), (3000, 0.15, 0), (2500, 0.1, 2)]
+variants = [(2500, 0.1, 2), (2500, 0.1, 3), (2500, 0.1, 4), (2500, 0.1, 5), (2500, 0.1, 6), (3500, 0.1, 2)]
 if len(sys.argv) > 1:
     variants = [tuple(float(v) if "." in v else int(v) for v in a.split(",")) for a in sys.argv[1:]]
 for steps, ls, seed in variants:

@@ -73,16 +73,19 @@ def test_sliding_window_bf16(cuda_device):
     assert min(dice32) > 0.97
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_blend_paths_bit_identical(cuda_device, monkeypatch, precision):
+@pytest.mark.parametrize("precision,shape", [("fp32", (100, 70, 80)), ("bf16", (100, 70, 80)), ("bf16", (100, 70, 86)),
+                                             ("bf16", (100, 70, 83))])
+def test_blend_paths_bit_identical(cuda_device, monkeypatch, precision, shape):
     """Deferred (gather) blend == read-modify-write blend, bit for bit (same fp32 ops, same order).
 
     Both modes must see the same head kernel for this to be a statement about the BLEND: the read-modify-write form
     runs the head on the plane-sweep kernel (conv_ps.cu), so the row-sweep head (conv_rs.cu, a different fp32
-    accumulation order inside the conv) is switched off for this network; the two heads are compared below."""
+    accumulation order inside the conv) is switched off for this network; the two heads are compared below.
+    Axis-2 extents 80 / 86 / 83 put the last window start at a multiple of 4 / 2 / 1: the streaming blend kernel with
+    4 and with 2 voxels per thread, and the warp-per-class kernel."""
     eng = _engine()
     onet, sd = make_oracle_net(3, 1, 10, seed=6)
-    vol = normalized_volume((100, 70, 80), seed=9)[None].to(cuda_device)
+    vol = normalized_volume(shape, seed=9)[None].to(cuda_device)
     roi = (48, 48, 48)
     monkeypatch.setenv("SGM_NO_RS", "1")
     net = eng.UNetB200(sd, spatial_dims=3, in_channels=1, out_channels=10, device=cuda_device, precision=precision)

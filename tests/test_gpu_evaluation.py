@@ -48,31 +48,41 @@ def test_metrics_known_answers():
 
 
 def test_predict_with_labels_reports_dice_and_confusion(cuda_device, tmp_path, capsys):
-    """predict(test_labels=...) prints the reference's tables and writes mean_dice_<model>_generalized_score.txt (one
-    running mean per image, np.savetxt format) next to the label maps."""
+    """predict(test_labels=...) follows the reference's evaluation branch: the foreground crop comes from label > 0
+    (monai_unet.py:167), Dice / confusion counts are taken on the pre-processed (cropped) grid before Invertd
+    (:672-680), the tables are printed and mean_dice_<model>_generalized_score.txt holds one running mean per image
+    (np.savetxt format).  Expected values: the oracle composition with the same label."""
     import json
 
+    from oracle.predict import predict_volume as oracle_predict
     from segmantic_b200.image import nifti
     from segmantic_b200.seg.monai_unet import predict
     from segmantic_b200.synthetic import synthetic_lightning_checkpoint
+    from tests.helpers import make_oracle_net
     ck = synthetic_lightning_checkpoint(num_classes=3, num_channels=1, spatial_dims=3, spatial_size=[16, 16, 16],
                                         seed=12, **SMALL)
     torch.save(ck, tmp_path / "model.ckpt")
     (tmp_path / "model.json").write_text(json.dumps({"channels": [16, 32, 48], "strides": [2, 2]}))
+    onet, _ = make_oracle_net(3, 1, 3, seed=12, **SMALL)
     aff = osp.itk_geometry_to_ras_affine((1.0, 1.0, 1.0), (0.0, 0.0, 0.0), np.eye(3).flatten())
-    imgs, labs = [], []
+    imgs, labs, raws, gts = [], [], [], []
     for i in range(2):
-        raw = (normalized_volume((36, 32, 24), seed=50 + i) * 40.0 + 10.0)[0].numpy()
-        nifti.write(tmp_path / f"img{i}.nii.gz", raw, aff)
+        raw = (normalized_volume((36, 32, 24), seed=50 + i) * 40.0 + 10.0)[0]
+        nifti.write(tmp_path / f"img{i}.nii.gz", raw.numpy(), aff)
         imgs.append(tmp_path / f"img{i}.nii.gz")
+        raws.append(raw)
     out = tmp_path / "pass1"
     predict(tmp_path / "model.ckpt", imgs, None, out, {"Bone": 1, "Fat": 2})
-    # ground truth = the prediction itself for image 0 (Dice 1), a shifted copy for image 1 (Dice < 1)
+    # ground truth = the first pass's prediction (image 1: shifted), zero outside a box that is smaller than the image
     for i in range(2):
         lab, _, _ = nifti.read(out / f"img{i}.nii.gz")
         gt = lab[0] if i == 0 else np.roll(lab[0], 2, axis=0)
-        nifti.write(tmp_path / f"lab{i}.nii.gz", gt.astype(np.float32), aff)
+        box = np.zeros_like(gt)
+        box[4:30, 3:27, 2:21] = 1
+        gt = (gt * box).astype(np.float32)
+        nifti.write(tmp_path / f"lab{i}.nii.gz", gt, aff)
         labs.append(tmp_path / f"lab{i}.nii.gz")
+        gts.append(torch.from_numpy(gt))
     capsys.readouterr()
     out2 = tmp_path / "pass2"
     predict(tmp_path / "model.ckpt", imgs, labs, out2, {"Bone": 1, "Fat": 2})
@@ -80,11 +90,20 @@ def test_predict_with_labels_reports_dice_and_confusion(cuda_device, tmp_path, c
     assert "Class Dice:" in text and "Total Conf. Matrix Metrics:" in text and "Bone" in text and "sensitivity" in text
     scores = np.atleast_1d(np.loadtxt(out2 / "mean_dice_model_generalized_score.txt", delimiter=","))
     assert scores.shape == (2,)
-    pred0, _, _ = nifti.read(out2 / "img0.nii.gz")
-    pred1, _, _ = nifti.read(out2 / "img1.nii.gz")
-    gt1, _, _ = nifti.read(labs[1])
-    d0 = oe.class_dice(oe.confusion_matrix(3, pred0[0], pred0[0]))
-    d1 = oe.class_dice(oe.confusion_matrix(3, pred1[0], gt1[0]))
-    assert np.isclose(scores[0], np.nanmean(d0)) and np.isclose(scores[1], np.nanmean([np.nanmean(d0), np.nanmean(d1)]))
-    cm1 = np.loadtxt(out2 / "img1_confusion.csv", delimiter=",", dtype=np.int64)
-    assert np.array_equal(cm1, oe.confusion_matrix(3, pred1[0], gt1[0]))
+    per_image = []
+    for i in range(2):
+        ref_lab, _, pred_net, label_net = oracle_predict(onet, raws[i][None], aff, (), roi=(16, 16, 16), label=gts[i])
+        cm_ref = oe.confusion_matrix(3, pred_net.numpy(), label_net.numpy())
+        cm = np.loadtxt(out2 / f"img{i}_confusion.csv", delimiter=",", dtype=np.int64)
+        assert cm.sum() == cm_ref.sum() == label_net.numel()           # scored on the CROPPED grid
+        assert label_net.numel() < raws[i].numel()
+        assert np.abs(cm - cm_ref).sum() <= 0.004 * cm.sum()            # argmax near-ties only
+        per_image.append(np.nanmean(oe.class_dice(cm)))
+        pred, _, _ = nifti.read(out2 / f"img{i}.nii.gz")
+        assert float((pred[0] != ref_lab.numpy()).mean()) < 2e-3
+        outside = np.ones_like(pred[0], dtype=bool)
+        nz = np.argwhere(gts[i].numpy() > 0)
+        lo_, hi_ = nz.min(0), nz.max(0) + 1
+        outside[lo_[0]:hi_[0], lo_[1]:hi_[1], lo_[2]:hi_[2]] = False
+        assert not pred[0][outside].any()                               # inverse crop: label 0 outside the label's box
+    assert np.isclose(scores[0], per_image[0]) and np.isclose(scores[1], np.mean(per_image))

@@ -8,7 +8,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("group", ["s1", "ps", "s2", "t2", "cs", "torch"])
+@pytest.mark.parametrize("group", ["s1", "ps", "s2", "t2", "cs", "torch", "c20"])
 def test_tc_layers_match_cuda_core_kernels(cuda_device, group):
     from tests import diag_tc_layers
 

@@ -34,11 +34,16 @@ def test_predict_volume_with_spacing_matches_oracle_and_golden(cuda_device, inve
     onet, sd = make_oracle_net(3, 1, 3, seed=12, **SMALL)
     raw = normalized_volume((48, 40, 12), seed=23) * 100.0 + 50.0
     aff = osp.itk_geometry_to_ras_affine((0.5, 0.5, 3.0), (-12.0, -10.0, 0.0), np.eye(3).flatten())
-    ref, ref_logits = oracle_predict(onet, raw, aff, (1.0, 1.0, 1.0), roi=(16, 16, 16), invert=invert)
+    ref, ref_logits, gap = oracle_predict(onet, raw, aff, (1.0, 1.0, 1.0), roi=(16, 16, 16), invert=invert,
+                                          return_gap=True)
     lab = predict_volume(_net(sd, cuda_device), raw, aff, (1.0, 1.0, 1.0), invert=invert, precision="fp32")
     assert lab.shape == ref.shape == (48, 40, 12) and lab.dtype == torch.uint8
-    # label maps are bit-exact except at argmax / nearest-neighbour near-ties (documented exception)
-    assert float((lab != ref).float().mean()) < 2e-3
+    # label maps are bit-exact except at argmax near-ties (documented exception): every mismatch sits on a voxel whose
+    # oracle top-2 logit gap is below 1e-3 of the logit range (fp32 summation order), and there are few of them
+    bad = lab != ref
+    tol = 1e-3 * float(ref_logits.abs().max())
+    assert int((bad & (gap > tol)).sum()) == 0, f"{int((bad & (gap > tol)).sum())} mismatches outside near-ties"
+    assert float(bad.float().mean()) < 2e-3
     assert float((lab.numpy() != GOLD[f"predict_{invert}_mode"]).mean()) < 2e-3
 
 
@@ -46,9 +51,26 @@ def test_predict_volume_without_spacing_is_exact_outside_ties(cuda_device):
     from segmantic_b200.seg.monai_unet import predict_volume
     onet, sd = make_oracle_net(3, 1, 3, seed=12, **SMALL)
     raw = normalized_volume((40, 36, 28), seed=31) * 30.0 + 5.0
-    ref, logits = oracle_predict(onet, raw, None, (), roi=(16, 16, 16), overlap=0.5, mode="gaussian")
+    ref, logits, gap = oracle_predict(onet, raw, None, (), roi=(16, 16, 16), overlap=0.5, mode="gaussian", return_gap=True)
     lab = predict_volume(_net(sd, cuda_device), raw, None, (), overlap=0.5, mode="gaussian", precision="fp32")
-    assert float((lab != ref).float().mean()) < 1e-3
+    bad = lab != ref
+    assert int((bad & (gap > 1e-3 * float(logits.abs().max()))).sum()) == 0   # mismatches only at argmax near-ties
+    assert float(bad.float().mean()) < 1e-3
+
+
+def test_predict_volumes_pipelined_equals_per_image_calls(cuda_device):
+    """predict_volumes (uploads / downloads of neighbouring images overlapped with the prediction of the current one,
+    the loop of predict() over its images) yields exactly what predict_volume returns image by image."""
+    from segmantic_b200.seg.monai_unet import predict_volume, predict_volumes
+    _, sd = make_oracle_net(3, 1, 3, seed=12, **SMALL)
+    net = _net(sd, cuda_device)
+    imgs = [normalized_volume((40 + 4 * i, 36, 28), seed=40 + i) * 30.0 + 5.0 for i in range(4)]
+    kw = dict(overlap=0.5, mode="gaussian", precision="bf16")
+    one_by_one = [predict_volume(net, im, None, (), **kw) for im in imgs]
+    piped = list(predict_volumes(net, imgs, None, (), **kw))
+    assert len(piped) == len(imgs)
+    for a, b in zip(one_by_one, piped):
+        assert a.shape == b.shape and torch.equal(a, b)
 
 
 def test_predict_files_and_cli(cuda_device, tmp_path):

@@ -308,3 +308,18 @@ def test_reference_image_order_fixture():
     im3d_f = array_view_reverse_ordering(im3d)
     assert im3d_f.flags.owndata is False and im3d.shape == im3d_f.shape[::-1]
     assert all(im3d[k, j, i] == im3d_f[i, j, k] for k in range(12) for j in range(13) for i in range(14))
+
+
+def test_segmantic_import_shim_and_console_script():
+    """`segmantic.*` imports of the reference resolve to the drop-in, and pyproject.toml declares the reference's
+    console script (`segmantic-unet`, /root/reference/pyproject.toml:64-65)."""
+    import segmantic_b200.seg.monai_unet as impl
+    from segmantic.commands.monai_unet_cli import main
+    from segmantic.image.processing import resample, resample_to_ref
+    from segmantic.seg import monai_unet
+    assert monai_unet is impl and callable(monai_unet.predict) and callable(main)
+    assert callable(resample) and callable(resample_to_ref)
+    text = open(os.path.join(ROOT, "pyproject.toml")).read()
+    assert 'segmantic-unet = "segmantic_b200.commands.monai_unet_cli:main"' in text
+    with pytest.raises(ImportError):
+        import segmantic.seg.dataset  # noqa: F401  (not on the prediction path: absent, as documented)
