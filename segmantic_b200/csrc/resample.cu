@@ -224,6 +224,113 @@ __global__ void __launch_bounds__(256, 4) trilinear_brick_kernel(const TriArgs a
   }
 }
 
+// ---- axis-aligned maps without staging: separable per-axis tables + one warp per output row.
+// The gather kernel above spends most of its instructions on two 64-bit integer divisions per voxel and on recomputing
+// the three float64 source coordinates, floors and weights that depend on ONE output index each.  For diagonal maps a
+// table kernel evaluates those statements once per output index of every axis (the same expressions: bit-identical
+// results), and the main kernel walks output rows -- the axis-0 / axis-1 entries are warp-uniform, the axis-2 entries
+// come from the L1-resident table, row addressing is 32-bit.
+struct SepTables {
+  int* idx;        // [od0 | od1 | od2] floor of the clipped source coordinate
+  double* w0;      // weight of the lower neighbour
+  double* w1;      // weight of the upper neighbour
+};
+
+__global__ void trilinear_tables_kernel(const TriArgs a, SepTables t) {
+  const int n = a.od0 + a.od1 + a.od2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int ax = i < a.od0 ? 0 : (i < a.od0 + a.od1 ? 1 : 2);
+    const int o = i - (ax == 0 ? 0 : (ax == 1 ? a.od0 : a.od0 + a.od1));
+    // the statements of trilinear_kernel with the other two output indices at 0 (their coefficients are 0.0)
+    const int o0 = ax == 0 ? o : 0, o1 = ax == 1 ? o : 0, o2 = ax == 2 ? o : 0;
+    double c;
+    if (ax == 0) c = a.m[0] * o0 + a.m[1] * o1 + a.m[2] * o2 + a.m[3];
+    else if (ax == 1) c = a.m[4] * o0 + a.m[5] * o1 + a.m[6] * o2 + a.m[7];
+    else c = a.m[8] * o0 + a.m[9] * o1 + a.m[10] * o2 + a.m[11];
+    c = clipd(c, ax == 0 ? a.id0 : (ax == 1 ? a.id1 : a.id2));
+    const double f = floor(c);
+    t.idx[i] = (int)f;
+    t.w1[i] = c - f;
+    t.w0[i] = (f + 1.0) - c;
+  }
+}
+
+template <bool ARGMAX>
+__global__ void __launch_bounds__(256) trilinear_sep_kernel(const TriArgs a, const SepTables t) {
+  const long long ovox = (long long)a.od0 * a.od1 * a.od2;
+  const long long ivox = (long long)a.id0 * a.id1 * a.id2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int nrows = a.od0 * a.od1;
+  const int* ix2 = t.idx + a.od0 + a.od1;
+  const double* w02 = t.w0 + a.od0 + a.od1;
+  const double* w12 = t.w1 + a.od0 + a.od1;
+  for (int row = blockIdx.x * nwarps + warp; row < nrows; row += gridDim.x * nwarps) {
+    const int o0 = row / a.od1, o1 = row - o0 * a.od1;
+    const int z0 = __ldg(t.idx + o0), y0 = __ldg(t.idx + a.od0 + o1);
+    const int z1 = z0 + 1, y1 = y0 + 1;
+    const double wz0 = __ldg(t.w0 + o0), wz1 = __ldg(t.w1 + o0);
+    const double wy0 = __ldg(t.w0 + a.od0 + o1), wy1 = __ldg(t.w1 + a.od0 + o1);
+    const bool by1 = y1 < a.id1, bz1 = z1 < a.id0;
+    // row bases of the four (z, y) source rows (clamped rows are never read: their ok flags are false)
+    const int r00 = (z0 * a.id1 + y0) * a.id2;
+    const int r01 = by1 ? (z0 * a.id1 + y1) * a.id2 : r00;
+    const int r10 = bz1 ? (z1 * a.id1 + y0) * a.id2 : r00;
+    const int r11 = (bz1 && by1) ? (z1 * a.id1 + y1) * a.id2 : r00;
+    const long long vrow = (long long)row * a.od2;
+    for (int o2 = lane; o2 < a.od2; o2 += 32) {
+      const int x0 = __ldg(ix2 + o2), x1 = x0 + 1;
+      const double wx0 = __ldg(w02 + o2), wx1 = __ldg(w12 + o2);
+      const bool bx1 = x1 < a.id2;
+      // ATen order: tnw tne tsw tse bnw bne bsw bse  (t/b = z0/z1, n/s = y0/y1, w/e = x0/x1)
+      const double w[8] = {__dmul_rn(__dmul_rn(wx0, wy0), wz0), __dmul_rn(__dmul_rn(wx1, wy0), wz0),
+                           __dmul_rn(__dmul_rn(wx0, wy1), wz0), __dmul_rn(__dmul_rn(wx1, wy1), wz0),
+                           __dmul_rn(__dmul_rn(wx0, wy0), wz1), __dmul_rn(__dmul_rn(wx1, wy0), wz1),
+                           __dmul_rn(__dmul_rn(wx0, wy1), wz1), __dmul_rn(__dmul_rn(wx1, wy1), wz1)};
+      const bool ok[8] = {true, bx1, by1, bx1 && by1, bz1, bz1 && bx1, bz1 && by1, bz1 && by1 && bx1};
+      const int xe = bx1 ? x1 : x0;
+      const int off[8] = {r00 + x0, r00 + xe, r01 + x0, r01 + xe, r10 + x0, r10 + xe, r11 + x0, r11 + xe};
+      float best = 0.f;
+      int arg = 0;
+      for (int c = 0; c < a.channels; ++c) {
+        const float* src = a.in + c * ivox;
+        double sacc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (ok[k]) sacc = __dadd_rn(sacc, __dmul_rn((double)__ldg(src + off[k]), w[k]));
+        const float r = (float)sacc;
+        if (ARGMAX) {
+          if (c == 0 || r > best) best = r, arg = c;
+        } else {
+          a.out[c * ovox + vrow + o2] = r;
+        }
+      }
+      if (ARGMAX) a.labels[vrow + o2] = (uint8_t)arg;
+    }
+  }
+}
+
+static bool tri_diagonal(const TriArgs& a) {
+  if (a.m[1] != 0.0 || a.m[2] != 0.0 || a.m[4] != 0.0 || a.m[6] != 0.0 || a.m[8] != 0.0 || a.m[9] != 0.0) return false;
+  return (long long)a.id0 * a.id1 * a.id2 < (1LL << 31) && (long long)a.od0 * a.od1 < (1LL << 31);
+}
+
+template <bool ARGMAX>
+static int launch_trilinear_sep(const TriArgs& a, cudaStream_t st) {
+  const int n = a.od0 + a.od1 + a.od2;
+  char* buf = nullptr;
+  SGM_CUDA_CHECK(cudaMallocAsync((void**)&buf, (size_t)n * 24, st));  // doubles first (8-byte aligned), then the ints
+  SepTables t;
+  t.w0 = (double*)buf, t.w1 = t.w0 + n, t.idx = (int*)(t.w1 + n);
+  trilinear_tables_kernel<<<(n + 255) / 256, 256, 0, st>>>(a, t);
+  const int nrows = a.od0 * a.od1;
+  const int grid = std::max(1, std::min((nrows + 7) / 8, 148 * 8));
+  trilinear_sep_kernel<ARGMAX><<<grid, 256, 0, st>>>(a, t);
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(buf, st);
+  SGM_CUDA_CHECK(e);
+  return SGM_OK;
+}
+
 // ------------------------------------------------------------------------------------------ ITK
 struct ItkArgs {
   const void* in;
@@ -368,6 +475,94 @@ __global__ void __launch_bounds__(256) itk_resample_vec_kernel(const ItkArgs a) 
   }
 }
 
+// ---- axis-aligned nearest neighbour: separable index tables.
+// With diagonal index<->physical matrices (identity directions: Spacingd's inverse, resample_to_ref between images of
+// the same orientation) the continuous index along input axis r depends on the output index along axis r alone: in the
+// scan-line formula  c[r] = cs[r] + alpha * (ce[r] - cs[r])  the other output indices enter through products with exact
+// zeros, and for r != 0 the line's end points coincide (ce[r] - cs[r] = +0).  A table kernel evaluates THE SAME device
+// functions (itk_cindex, the alpha division, the inside test, floor(c + 0.5)) once per output index of every axis --
+// bit-identical source indices by construction -- and the main kernel is a pure gather: a warp-coalesced row of
+// table look-ups and byte loads instead of ~45 float64 operations, one float64 division and two 64-bit integer
+// divisions per voxel.
+__global__ void itk_tables_kernel(const ItkArgs a, int* tab) {
+  // tab: [out_n0 | out_n1 | out_n2] source index per output index, -1 = outside the input buffer
+  const int n0 = a.out_n[0], n1 = a.out_n[1], n2 = a.out_n[2];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n0 + n1 + n2; i += gridDim.x * blockDim.x) {
+    const int r = i < n0 ? 0 : (i < n0 + n1 ? 1 : 2);
+    const int o = i - (r == 0 ? 0 : (r == 1 ? n0 : n0 + n1));
+    const int ox = r == 0 ? o : 0, oy = r == 1 ? o : 0, oz = r == 2 ? o : 0;
+    double cs[3], ce[3];
+    itk_cindex(a, 0.0, (double)oy, (double)oz, cs);
+    itk_cindex(a, (double)a.out_n[0], (double)oy, (double)oz, ce);
+    const double alpha = (double)ox / (double)a.out_n[0];
+    const double c = __dadd_rn(cs[r], __dmul_rn(alpha, __dadd_rn(ce[r], -cs[r])));
+    const bool inside = (c >= -0.5) && (c < (double)a.in_n[r] - 0.5);
+    const int idx = min(max((int)floor(c + 0.5), 0), a.in_n[r] - 1);
+    tab[i] = inside ? idx : -1;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) itk_nearest_sep_kernel(const ItkArgs a, const int* __restrict__ tab) {
+  extern __shared__ int s_tx[];  // the axis-0 table: shared by every scan line
+  const int n0 = a.out_n[0], n1 = a.out_n[1], n2 = a.out_n[2];
+  for (int i = threadIdx.x; i < n0; i += blockDim.x) s_tx[i] = tab[i];
+  __syncthreads();
+  const T* in = reinterpret_cast<const T*>(a.in);
+  T* out = reinterpret_cast<T*>(a.out);
+  const T defv = itk_cast<T>(a.defval);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int nlines = n1 * n2;
+  constexpr int VP = 4;
+  struct alignas(sizeof(T) * VP) Pack { T v[VP]; };
+  const bool packed = (n0 % VP == 0) && ((uintptr_t)out % (sizeof(T) * VP) == 0);
+  for (int line = blockIdx.x * nwarps + warp; line < nlines; line += gridDim.x * nwarps) {  // one warp per scan line
+    const int oz = line / n1, oy = line - oz * n1;
+    const int iy = __ldg(tab + n0 + oy), iz = __ldg(tab + n0 + n1 + oz);
+    T* orow = out + (long long)line * n0;
+    const bool row_in = iy >= 0 && iz >= 0;
+    const T* irow = in + (row_in ? ((long long)iz * a.in_n[1] + iy) * a.in_n[0] : 0);
+    if (packed) {
+      for (int xq = lane; xq < n0 / VP; xq += 32) {
+        const int4 ix = *reinterpret_cast<const int4*>(s_tx + xq * VP);
+        Pack r;
+        r.v[0] = (row_in && ix.x >= 0) ? __ldg(irow + ix.x) : defv;
+        r.v[1] = (row_in && ix.y >= 0) ? __ldg(irow + ix.y) : defv;
+        r.v[2] = (row_in && ix.z >= 0) ? __ldg(irow + ix.z) : defv;
+        r.v[3] = (row_in && ix.w >= 0) ? __ldg(irow + ix.w) : defv;
+        *reinterpret_cast<Pack*>(orow + xq * VP) = r;
+      }
+    } else {
+      for (int x = lane; x < n0; x += 32) {
+        const int ix = s_tx[x];
+        orow[x] = (row_in && ix >= 0) ? __ldg(irow + ix) : defv;
+      }
+    }
+  }
+}
+
+static bool itk_diagonal(const ItkArgs& a) {
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c)
+      if (r != c && (a.i2p[r * 3 + c] != 0.0 || a.p2i[r * 3 + c] != 0.0)) return false;
+  return true;
+}
+
+template <typename T>
+static int launch_itk_sep(const ItkArgs& a, cudaStream_t st) {
+  const int n = a.out_n[0] + a.out_n[1] + a.out_n[2];
+  int* tab = nullptr;
+  SGM_CUDA_CHECK(cudaMallocAsync((void**)&tab, (size_t)n * sizeof(int), st));
+  itk_tables_kernel<<<(n + 255) / 256, 256, 0, st>>>(a, tab);
+  const int nlines = a.out_n[1] * a.out_n[2];
+  const int grid = std::max(1, std::min((nlines + 7) / 8, 148 * 8));
+  itk_nearest_sep_kernel<T><<<grid, 256, (size_t)a.out_n[0] * sizeof(int), st>>>(a, tab);
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(tab, st);
+  SGM_CUDA_CHECK(e);
+  return SGM_OK;
+}
+
 // ------------------------------------------------------------------------ normalize / bbox
 constexpr int RED_BLOCKS = 1024;
 
@@ -467,7 +662,7 @@ int grid_for(long long n) {
 // Tile search for trilinear_brick_kernel: T0*T1*T2 = 256 threads, source box (times the channels staged per
 // pass) within 48 KB, minimise input voxels staged per output voxel.
 static bool brick_plan(const TriArgs& a, BrickPlan& p) {
-  if (getenv("SGM_NO_RESAMPLE_BRICK")) return false;
+  if (getenv("SGM_NO_RESAMPLE_BRICK") || getenv("SGM_RESAMPLE_SEP_ALWAYS")) return false;
   // measured on the configs[2] shapes (bench.py roofline_resample): 10-class inverse 6.7 -> 3.0 ms, but the single-channel
   // forward resample 0.38 -> 0.62 ms (one channel does not amortise the tile's stage -> barrier -> compute chain)
   if (a.channels < 4 && !getenv("SGM_RESAMPLE_BRICK_ALWAYS")) return false;
@@ -524,6 +719,8 @@ static int launch_trilinear(const TriArgs& a, cudaStream_t st) {
     const size_t smem = (size_t)p.CC * p.S0 * p.S1 * p.S2 * sizeof(float);
     const int grid = (int)std::min<long long>(ntiles, 148LL * 32);
     trilinear_brick_kernel<ARGMAX><<<grid, p.T0 * p.T1 * p.T2, smem, st>>>(a, p);
+  } else if (tri_diagonal(a) && !getenv("SGM_NO_RESAMPLE_SEP")) {
+    return launch_trilinear_sep<ARGMAX>(a, st);
   } else {
     trilinear_kernel<ARGMAX><<<grid_for(ovox), 256, 0, st>>>(a);
   }
@@ -579,6 +776,18 @@ extern "C" int32_t sgm_resample_itk(const void* in_dev, int32_t dtype, const int
   const long long ovox = (long long)a.out_n[0] * a.out_n[1] * a.out_n[2];
   cudaStream_t st = (cudaStream_t)stream;
   const bool no_vec = getenv("SGM_NO_RESAMPLE_VEC") != nullptr;  // A/B switch (tests compare the two kernels for equality)
+  // axis-aligned nearest neighbour (the label path): separable index tables + a pure gather, bit-identical
+  if (nearest && !no_vec && !getenv("SGM_NO_RESAMPLE_SEP") && itk_diagonal(a) && a.out_n[0] <= 12288 &&
+      (long long)a.out_n[1] * a.out_n[2] < (1LL << 31)) {
+    switch (dtype) {
+      case 0: return launch_itk_sep<uint8_t>(a, st);
+      case 1: return launch_itk_sep<int16_t>(a, st);
+      case 2: return launch_itk_sep<uint16_t>(a, st);
+      case 3: return launch_itk_sep<float>(a, st);
+      case 4: return launch_itk_sep<int32_t>(a, st);
+      default: set_error("resample_itk: unsupported dtype code %d", dtype); return SGM_ERR_UNSUPPORTED;
+    }
+  }
   const bool vec = !no_vec && a.out_n[0] % 4 == 0 && ((uintptr_t)out_dev % 16) == 0;
   const int g = grid_for(vec ? ovox / 4 : ovox);
   switch (dtype) {

@@ -100,9 +100,9 @@ _CACHE: Dict[tuple, Dict[str, torch.Tensor]] = {}
 
 
 # The pinned recipe (tests/explore_confident.py swept steps / label smoothing / seeds on a B200 at the full configs[1]
-# size): label smoothing keeps the logits within +-8 (the bf16 error of a logit scales with the logit range), 2500
-# steps reach 99.8 % accuracy on the phantom.
-RECIPE = dict(steps=2500, label_smoothing=0.1, seed=2)
+# size): label smoothing keeps the logits within +-8 (the bf16 error of a logit scales with the logit range), 3500
+# steps reach 99.9 % accuracy on the phantom (min Dice of the bf16 device path against the fp32 oracle 0.99937).
+RECIPE = dict(steps=3500, label_smoothing=0.1, seed=2)
 
 
 def confident_state_dict(n_classes: int = 10, steps: int = RECIPE["steps"], seed: int = RECIPE["seed"],

@@ -114,8 +114,8 @@ def test_normalize_and_bbox(cuda_device):
 @pytest.mark.parametrize("channels", [1, 3, 10, 37])
 @pytest.mark.parametrize("case", ["up_xy_down_z", "down_xy_up_z", "shift_only", "flip_scale", "coarse"])
 def test_trilinear_brick_kernel_matches_gather_kernel(cuda_device, monkeypatch, channels, case):
-    """The shared-memory-staged trilinear kernel (axis-aligned transforms) against the one-thread-per-voxel gather
-    kernel it replaces: same float64 statements per voxel, so outputs and fused-argmax labels are EQUAL -- for
+    """The shared-memory-staged trilinear kernel and the separable-table row kernel (axis-aligned transforms) against
+    the one-thread-per-voxel gather kernel they replace: same float64 statements per voxel, so outputs and fused-argmax labels are EQUAL -- for
     up / down scaling, pure shifts, negative scales, clipped borders, several channel passes, ragged tiles."""
     from segmantic_b200.seg import transforms as T
     g = torch.Generator().manual_seed(channels)
@@ -131,13 +131,18 @@ def test_trilinear_brick_kernel_matches_gather_kernel(cuda_device, monkeypatch, 
     xf[3, 3] = 1.0
     for a in range(3):
         xf[a, a], xf[a, 3] = diag[a], off[a]
-    monkeypatch.setenv("SGM_RESAMPLE_BRICK_ALWAYS", "1")  # few channels take the gather kernel by default
+    monkeypatch.setenv("SGM_RESAMPLE_BRICK_ALWAYS", "1")  # few channels take the table kernel by default
     monkeypatch.setenv("SGM_NO_RESAMPLE_BRICK", "1")
+    monkeypatch.setenv("SGM_NO_RESAMPLE_SEP", "1")         # the one-thread-per-voxel gather kernel: the reference form
     ref = T.resample_index_affine(img, xf, dst)
     ref_lab = T.resample_index_affine_argmax(img, xf, dst)
-    monkeypatch.delenv("SGM_NO_RESAMPLE_BRICK")
+    monkeypatch.delenv("SGM_NO_RESAMPLE_SEP")              # separable tables + one warp per output row
+    sep = T.resample_index_affine(img, xf, dst)
+    sep_lab = T.resample_index_affine_argmax(img, xf, dst)
+    monkeypatch.delenv("SGM_NO_RESAMPLE_BRICK")            # shared-memory-staged tiles
     out = T.resample_index_affine(img, xf, dst)
     lab = T.resample_index_affine_argmax(img, xf, dst)
+    assert torch.equal(sep, ref) and torch.equal(sep_lab, ref_lab)
     assert torch.equal(out, ref)
     assert torch.equal(lab, ref_lab)
     assert torch.equal(lab.long(), out.argmax(0))
