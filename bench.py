@@ -347,15 +347,20 @@ def run_b200(args):
         step()
     # settle: extra untimed steps until two consecutive ones agree within 5 % (allocator growth, clock ramp, the
     # sampler's NVML start-up); at most 10
+    # (N > 1: a FIXED number of settle steps -- every step is a collective exchange between the ranks, so all ranks must
+    # run the same number of them; a per-rank, timing-dependent exit left the ranks with different step counts.)
     prev = None
-    for _ in range(10):
+    for it in range(10):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         step()
         e1.record()
         torch.cuda.synchronize(dev)
         cur = e0.elapsed_time(e1)
-        if prev is not None and abs(cur - prev) <= 0.05 * prev:
+        if world > 1:
+            if it >= 3:
+                break
+        elif prev is not None and abs(cur - prev) <= 0.05 * prev:
             break
         prev = cur
     net.check()
