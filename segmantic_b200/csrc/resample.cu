@@ -719,7 +719,9 @@ static int launch_trilinear(const TriArgs& a, cudaStream_t st) {
     const size_t smem = (size_t)p.CC * p.S0 * p.S1 * p.S2 * sizeof(float);
     const int grid = (int)std::min<long long>(ntiles, 148LL * 32);
     trilinear_brick_kernel<ARGMAX><<<grid, p.T0 * p.T1 * p.T2, smem, st>>>(a, p);
-  } else if (tri_diagonal(a) && !getenv("SGM_NO_RESAMPLE_SEP")) {
+  } else if (getenv("SGM_RESAMPLE_SEP") && tri_diagonal(a) && !getenv("SGM_NO_RESAMPLE_SEP")) {
+    // OPT-IN: on the configs[2] forward Spacing (1 channel) the row kernel measured 3.5 ms against 0.38 ms of the
+    // gather kernel -- kept for the equality tests and further work, not on the default path.
     return launch_trilinear_sep<ARGMAX>(a, st);
   } else {
     trilinear_kernel<ARGMAX><<<grid_for(ovox), 256, 0, st>>>(a);
@@ -777,7 +779,10 @@ extern "C" int32_t sgm_resample_itk(const void* in_dev, int32_t dtype, const int
   cudaStream_t st = (cudaStream_t)stream;
   const bool no_vec = getenv("SGM_NO_RESAMPLE_VEC") != nullptr;  // A/B switch (tests compare the two kernels for equality)
   // axis-aligned nearest neighbour (the label path): separable index tables + a pure gather, bit-identical
-  if (nearest && !no_vec && !getenv("SGM_NO_RESAMPLE_SEP") && itk_diagonal(a) && a.out_n[0] <= 12288 &&
+  // OPT-IN (SGM_RESAMPLE_SEP=1): measured on the configs[2] label map it is SLOWER than the 4-voxels-per-thread kernel
+  // (0.27 vs 0.14 ms: the per-call table allocation and kernel cost more than the float64 work they save).
+  const bool sep_on = getenv("SGM_RESAMPLE_SEP") != nullptr;
+  if (sep_on && nearest && !no_vec && !getenv("SGM_NO_RESAMPLE_SEP") && itk_diagonal(a) && a.out_n[0] <= 12288 &&
       (long long)a.out_n[1] * a.out_n[2] < (1LL << 31)) {
     switch (dtype) {
       case 0: return launch_itk_sep<uint8_t>(a, st);

@@ -132,6 +132,20 @@ def _infer_io_channels(sd, hp) -> dict:
     return out
 
 
+_PIPE_DEPTH = 4   # pinned result buffers in rotation (predict_volumes)
+
+
+def _pipe_state(eng) -> dict:
+    """Streams and buffer rings of the pipelined loop, created once per engine (re-created streams and per-volume
+    allocations of pinned / cross-stream device memory cost milliseconds each and stall the pipeline)."""
+    st = eng.__dict__.get("_pipe")
+    if st is None:
+        dev = eng.device
+        st = eng.__dict__["_pipe"] = dict(copy_in=torch.cuda.Stream(dev), copy_out=torch.cuda.Stream(dev),
+                                          dev_in={}, host_out={})
+    return st
+
+
 def predict_volumes(net: Net, images, affines=None, spacing: Sequence[float] = (), *, precision: str = "fp32",
                     **kwargs):
     """Pipelined ``predict_volume`` over a sequence of HOST images (the loop of ``predict()`` over ``test_images``,
@@ -140,15 +154,21 @@ def predict_volumes(net: Net, images, affines=None, spacing: Sequence[float] = (
     The z-score normalisation needs the whole volume before the first window can run, so the upload of ONE volume
     cannot overlap its own prediction; across volumes it can: the host->device copy of image ``i + 1`` (copy engine, its
     own stream, second device buffer) and the device->host copy of label map ``i - 1`` run while the SMs predict image
-    ``i``.  Every image still crosses PCIe exactly once in each direction; results are those of ``predict_volume``."""
+    ``i``.  Every image still crosses PCIe exactly once in each direction; results are those of ``predict_volume``.
+
+    Buffers are rings owned by the engine (two device input buffers and ``_PIPE_DEPTH`` pinned result buffers per
+    shape): a yielded label map is overwritten once ``_PIPE_DEPTH`` further results have been produced -- consume or
+    copy it before (``predict()`` writes every map to disk at once)."""
     eng = net.engine(precision)
     dev = eng.device
     images = list(images)
     affines = list(affines) if affines is not None else [None] * len(images)
     if not images:
         return
+    st = _pipe_state(eng)
     compute = torch.cuda.current_stream(dev)
-    copy_in, copy_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    copy_in, copy_out = st["copy_in"], st["copy_out"]
+    done_events = {}   # image index -> event: its prediction has finished on the compute stream
 
     def upload(i):
         src = images[i]
@@ -156,13 +176,24 @@ def predict_volumes(net: Net, images, affines=None, spacing: Sequence[float] = (
             return src, None
         if not src.is_pinned():
             src = src.pin_memory()
+        key = (tuple(src.shape), src.dtype)
+        ring = st["dev_in"].get(key)
+        if ring is None:
+            with torch.cuda.device(dev):
+                ring = st["dev_in"][key] = [torch.empty(src.shape, dtype=src.dtype, device=dev) for _ in range(2)]
+            torch.cuda.current_stream(dev).synchronize()   # (first use only) the buffers exist before another stream writes
+        d = ring[i % 2]
+        if i - 2 in done_events:        # the slot's previous user (image i - 2) has been predicted
+            copy_in.wait_event(done_events[i - 2])
+        else:                           # first uses of the slot in this call: nothing of an earlier call reads it any more
+            copy_in.wait_stream(compute)
         with torch.cuda.stream(copy_in):
-            d = src.to(dev, non_blocking=True)
+            d.copy_(src, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_in)
         return d, ev
 
-    pending = None          # (host label map, its copy event) of the previous image
+    pending = None          # (host label map, its copy event, device label map kept alive) of the previous image
     nxt = upload(0)
     for i in range(len(images)):
         cur, ev = nxt
@@ -171,21 +202,25 @@ def predict_volumes(net: Net, images, affines=None, spacing: Sequence[float] = (
             compute.wait_event(ev)
         lab = predict_volume(net, cur, affines[i], spacing, precision=precision, return_device=True, check=False,
                              **kwargs)
-        if ev is not None:
-            cur.record_stream(compute)
         done = torch.cuda.Event()
         done.record(compute)
-        host = torch.empty(lab.shape, dtype=lab.dtype, pin_memory=True)
+        done_events[i] = done
+        done_events.pop(i - 3, None)
+        okey = (tuple(lab.shape), lab.dtype)
+        oring = st["host_out"].get(okey)
+        if oring is None:
+            oring = st["host_out"][okey] = [torch.empty(lab.shape, dtype=lab.dtype, pin_memory=True)
+                                            for _ in range(_PIPE_DEPTH)]
+        host = oring[i % _PIPE_DEPTH]
+        copy_out.wait_event(done)
         with torch.cuda.stream(copy_out):
-            copy_out.wait_event(done)
             host.copy_(lab, non_blocking=True)
-            lab.record_stream(copy_out)
             out_ev = torch.cuda.Event()
             out_ev.record(copy_out)
         if pending is not None:
             pending[1].synchronize()
             yield pending[0]
-        pending = (host, out_ev)
+        pending = (host, out_ev, lab)
     pending[1].synchronize()
     eng.check()   # a tcgen05 pipeline timeout anywhere in the sequence raises here
     yield pending[0]

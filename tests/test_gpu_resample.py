@@ -133,12 +133,12 @@ def test_trilinear_brick_kernel_matches_gather_kernel(cuda_device, monkeypatch, 
         xf[a, a], xf[a, 3] = diag[a], off[a]
     monkeypatch.setenv("SGM_RESAMPLE_BRICK_ALWAYS", "1")  # few channels take the table kernel by default
     monkeypatch.setenv("SGM_NO_RESAMPLE_BRICK", "1")
-    monkeypatch.setenv("SGM_NO_RESAMPLE_SEP", "1")         # the one-thread-per-voxel gather kernel: the reference form
-    ref = T.resample_index_affine(img, xf, dst)
+    ref = T.resample_index_affine(img, xf, dst)            # the one-thread-per-voxel gather kernel: the reference form
     ref_lab = T.resample_index_affine_argmax(img, xf, dst)
-    monkeypatch.delenv("SGM_NO_RESAMPLE_SEP")              # separable tables + one warp per output row
+    monkeypatch.setenv("SGM_RESAMPLE_SEP", "1")            # separable tables + one warp per output row (opt-in)
     sep = T.resample_index_affine(img, xf, dst)
     sep_lab = T.resample_index_affine_argmax(img, xf, dst)
+    monkeypatch.delenv("SGM_RESAMPLE_SEP")
     monkeypatch.delenv("SGM_NO_RESAMPLE_BRICK")            # shared-memory-staged tiles
     out = T.resample_index_affine(img, xf, dst)
     lab = T.resample_index_affine_argmax(img, xf, dst)
@@ -166,5 +166,8 @@ def test_itk_resample_vector_kernel_bit_exact(cuda_device, monkeypatch, dtype, n
         monkeypatch.setenv("SGM_NO_RESAMPLE_VEC", "1")
         c = P.resample_to_ref(mov, ref, nearest)
         monkeypatch.delenv("SGM_NO_RESAMPLE_VEC")
-        assert np.array_equal(b.array, c.array)
+        monkeypatch.setenv("SGM_RESAMPLE_SEP", "1")   # opt-in: separable index tables + pure gather (nearest only)
+        d = P.resample_to_ref(mov, ref, nearest)
+        monkeypatch.delenv("SGM_RESAMPLE_SEP")
+        assert np.array_equal(b.array, c.array) and np.array_equal(b.array, d.array)
         assert np.array_equal(a.array, b.array)
