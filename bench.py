@@ -203,7 +203,8 @@ def make_block(seed=1):
     # OMP_NUM_THREADS=1, plain python uses every core), which moved the normalised volume by an ulp between the N = 1
     # and the N > 1 runs and with it a few thousand argmax near-ties (label checksums of configs[3], round 2)
     r64 = raw.double()
-    norm = ((r64 - r64.mean()) / r64.std(unbiased=False)).float()
+    m, sd = float(f"{float(r64.mean()):.12g}"), float(f"{float(r64.std(unbiased=False)):.12g}")  # thread-count independent
+    norm = ((r64 - m) / sd).float()
     return raw, norm
 
 
