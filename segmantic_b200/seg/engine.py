@@ -262,24 +262,15 @@ def _sw_run(net: UNetB200, vol: torch.Tensor, sched: Schedule, sw_batch_size: in
 def _sw_run_chunked(net: UNetB200, vol: torch.Tensor, sched: Schedule, sw_batch_size: int, return_logits: bool,
                     return_labels: bool, budget_bytes: int):
     """Deferred blend in chunks of the window list (see ``_sw_run``); ``None`` when no chunking fits ``budget_bytes``."""
-    from .sliding_window import window_partition
+    from .sliding_window import plan_chunks
 
     roivox = int(sched.roi[0]) * int(sched.roi[1]) * int(sched.roi[2])
     stride = net.out_channels * roivox * 4
     device_batch = max(int(sw_batch_size), int(os.environ.get("SGM_SW_BATCH", DEVICE_SW_BATCH)))
     with torch.cuda.device(net.device):
         net_ws = int(net._lib.sgm_unet_workspace_bytes(net._handle, _lib.i3(sched.roi), min(device_batch, sched.n_windows)))
-    parts = None
-    for nchunks in range(2, len(sched.starts[0]) + 1):
-        try:
-            cand = window_partition(sched, nchunks)
-        except ValueError:
-            break
-        held = sorted((p["w_hi"] - p["wb"]) * stride for p in cand)
-        # two exchange buffers alternate (chunk r blends from buffer r % 2 while chunk r + 1's seam is copied in)
-        if held[-1] + (held[-2] if len(held) > 1 else 0) + net_ws + (256 << 20) <= budget_bytes:
-            parts = cand
-            break
+    # two exchange buffers alternate (chunk r blends from buffer r % 2 while chunk r + 1's seam is copied in)
+    parts = plan_chunks(sched, stride, net_ws + (256 << 20), budget_bytes)
     if parts is None:
         return None
     size3 = sched.padded_size

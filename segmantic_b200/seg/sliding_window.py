@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import math
 from dataclasses import dataclass, field
-from typing import List, Sequence, Tuple
+from typing import Optional, List, Sequence, Tuple
 
 import torch
 
@@ -195,3 +195,19 @@ def window_partition(schedule: Schedule, world_size: int) -> List[dict]:
             raise ValueError("window_partition: a rank would need windows of two earlier ranks "
                              f"(world_size {world_size} too large for {n0} window rows); use slab_partition")
     return parts
+
+
+def plan_chunks(schedule: Schedule, bytes_per_window: int, fixed_bytes: int, budget_bytes: int) -> Optional[List[dict]]:
+    """Single-GPU chunking of a volume whose deferred-blend buffer exceeds the memory budget: the smallest number of
+    chunks of the window list (``window_partition``) such that the two alternating exchange buffers -- the largest and
+    the second largest ``(w_hi - wb) * bytes_per_window`` -- plus ``fixed_bytes`` (network workspace) fit
+    ``budget_bytes``.  ``None`` when no chunking fits (the caller falls back to the read-modify-write blend)."""
+    for nchunks in range(2, len(schedule.starts[0]) + 1):
+        try:
+            cand = window_partition(schedule, nchunks)
+        except ValueError:
+            return None
+        held = sorted((p["w_hi"] - p["wb"]) * int(bytes_per_window) for p in cand)
+        if held[-1] + (held[-2] if len(held) > 1 else 0) + int(fixed_bytes) <= int(budget_bytes):
+            return cand
+    return None

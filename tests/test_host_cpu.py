@@ -323,3 +323,52 @@ def test_segmantic_import_shim_and_console_script():
     assert 'segmantic-unet = "segmantic_b200.commands.monai_unet_cli:main"' in text
     with pytest.raises(ImportError):
         import segmantic.seg.dataset  # noqa: F401  (not on the prediction path: absent, as documented)
+
+
+def test_plan_chunks_for_volumes_beyond_hbm():
+    """Single-GPU chunking of BASELINE configs[3] (2100 windows x 20 classes x 96^3 x 4 B = 148 GB of deferred-blend
+    buffer): the smallest chunk count whose two alternating buffers fit the budget; chunks tile the window list."""
+    from segmantic_b200.seg.sliding_window import make_schedule, plan_chunks
+    sched = make_schedule((1024, 512, 512), (96, 96, 96), 0.5, "gaussian")
+    per_window = 20 * 96 ** 3 * 4
+    assert sched.n_windows == 2100 and sched.n_windows * per_window > 140e9
+    parts = plan_chunks(sched, per_window, 8 << 30, 140 << 30)
+    assert parts is not None and len(parts) == 3
+    assert parts[0]["w_lo"] == 0 and parts[-1]["w_hi"] == 2100
+    assert all(a["w_hi"] == b["w_lo"] and b["wb"] == a["send_lo"] for a, b in zip(parts, parts[1:]))
+    held = sorted((p["w_hi"] - p["wb"]) * per_window for p in parts)
+    assert held[-1] + held[-2] + (8 << 30) <= 140 << 30
+    assert len(plan_chunks(sched, per_window, 8 << 30, 60 << 30)) > 3          # a smaller budget -> more chunks
+    assert plan_chunks(sched, per_window, 8 << 30, 10 << 30) is None           # nothing fits: caller falls back
+
+
+def test_bench_block_is_thread_count_independent():
+    """bench.make_block normalises the synthetic block with float64, digit-rounded statistics: a float32 parallel
+    mean() depends on the number of host threads (torchrun sets OMP_NUM_THREADS=1), which fed the N = 1 and N > 1 runs
+    volumes that differed in the last bit."""
+    import bench
+    old = torch.get_num_threads()
+    try:
+        outs = []
+        for t in (1, max(2, old)):
+            torch.set_num_threads(t)
+            small = bench.VOL
+            bench.VOL = (64, 64, 64)
+            try:
+                outs.append(bench.make_block(seed=3)[1])
+            finally:
+                bench.VOL = small
+        assert torch.equal(outs[0], outs[1])
+    finally:
+        torch.set_num_threads(old)
+
+
+def test_predict_volumes_needs_a_cuda_device():
+    from segmantic_b200.seg.monai_unet import Net, predict_volumes
+    from segmantic_b200.synthetic import synthetic_state_dict
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only behaviour")
+    net = Net(num_classes=3, num_channels=1, spatial_dims=3, channels=(16, 32, 48), strides=(2, 2))
+    net.load_state_dict(synthetic_state_dict(3, 1, 3, (16, 32, 48), (2, 2), seed=1))
+    with pytest.raises(RuntimeError):
+        list(predict_volumes(net, [torch.zeros(1, 16, 16, 16)]))

@@ -219,3 +219,36 @@ def test_reference_fixtures_for_evaluation_and_ensemble():
     preds = torch.stack([torch.ones(3, dtype=torch.long), torch.tensor([2, 0, 2]), torch.tensor([2, 1, 0])])
     out = oens.select_best_ensemble(preds, {1: 0, 2: 1, 0: 2})
     assert out.tolist() == [2, 1, 0]
+
+
+def test_oracle_evaluation_branch_crops_by_label_and_scores_on_the_network_grid():
+    """default_preprocessing(keys=["image", "label"]) (monai_unet.py:151-176): CropForegroundd(source_key="label"), the
+    label through the same transforms, scoring on the pre-processed grid (:672-680)."""
+    onet, _ = make_oracle_net(3, 1, 3, seed=12, **SMALL)
+    raw = (normalized_volume((36, 32, 24), seed=50) * 40.0 + 10.0)[0]
+    aff = osp.itk_geometry_to_ras_affine((1.0, 1.0, 1.0), (0.0, 0.0, 0.0), np.eye(3).flatten())
+    gt = torch.zeros(36, 32, 24)
+    gt[4:30, 3:27, 2:21] = 1
+    gt[10:20, 10:20, 5:15] = 2
+    lab, logits, pred_net, label_net = predict_volume(onet, raw[None], aff, (), roi=(16, 16, 16), label=gt)
+    assert tuple(lab.shape) == (36, 32, 24) and tuple(pred_net.shape) == tuple(label_net.shape) == (26, 24, 19)
+    assert int((label_net == 2).sum()) == 1000 and int((label_net > 0).sum()) == 26 * 24 * 19
+    outside = torch.ones_like(lab, dtype=torch.bool)
+    outside[4:30, 3:27, 2:21] = False
+    assert not lab[outside].any()                       # inverse crop: zero outside the label's bounding box
+    # with Spacing the label is resampled bilinearly and truncated (.long()), as the reference does
+    lab2, _, pred2, label2 = predict_volume(onet, raw[None], aff, (2.0, 2.0, 2.0), roi=(16, 16, 16), label=gt)
+    assert tuple(pred2.shape) == tuple(label2.shape) == (14, 12, 10) and tuple(lab2.shape) == (36, 32, 24)
+    assert set(label2.unique().tolist()) <= {0, 1, 2}
+
+
+def test_oracle_tie_gap_follows_the_labels():
+    """return_gap: the top-2 logit gap behind every output label, through the same inverse transforms (+inf outside the
+    crop) -- what the GPU tests use to tell argmax near-ties from real disagreements."""
+    onet, _ = make_oracle_net(3, 1, 3, seed=12, **SMALL)
+    raw = normalized_volume((40, 36, 28), seed=31) * 30.0 + 5.0
+    lab, logits, gap = predict_volume(onet, raw, None, (), roi=(16, 16, 16), overlap=0.5, mode="gaussian", return_gap=True)
+    assert gap.shape == lab.shape and bool((gap >= 0).all())
+    inside = torch.isfinite(gap)
+    assert int(inside.sum()) == logits.shape[1] * logits.shape[2] * logits.shape[3]   # the cropped grid, nothing else
+    assert not lab[~inside].any()
