@@ -15,8 +15,10 @@
 // loop.  All row tiles of all G windows share every weight stage, so the filter bank is read G * tiles times less
 // often than before; TMEM is double-buffered by unit (two halves of 256 columns) so the epilogue of a unit (TMEM ->
 // bias / PReLU / residual -> bf16 CG8 stores) overlaps the MMAs of the next; barriers and TMEM are set up once.
-// Two issuer threads split the row tiles of a unit (tile % 2), so every accumulator receives its MMAs from ONE
-// thread in a fixed order: results are bit-identical from run to run and for every window batch.
+// Four issuer threads split the row tiles of a unit (tile % 4), so every accumulator receives its MMAs from ONE
+// thread in a fixed order -- results are bit-identical from run to run and for every window batch -- while the ~6 clk
+// per dependent instruction of a single issuing thread no longer gates the tensor pipe (measured: 49 clk per N = 64 MMA
+// against 175 in the one-CTA-per-brick kernel; profiles/r02_cs_notes.md).
 //
 // MMA cost (tests/ubench_mma.cu): max(N / 2, 32 + N / 4) clk for M = 128, K = 16 -- shared-memory operand reads below
 // N = 128, the tensor pipe above: N = 64 runs at 67 % and N = 128 at 100 % of the tensor rate.
@@ -283,7 +285,7 @@ cs_conv_kernel(const __grid_constant__ CsArgs a, const __grid_constant__ CUtenso
     }
     __syncwarp();
   } else {
-    // ===================== epilogue: warp = (group eg, lane quarter q); group eg owns tiles tt % 2 == eg =====================
+    // ===================== epilogue: warp = (group eg, lane quarter q4); group eg owns tiles tt % 2 == eg =====================
     const int q4 = warp & 3, eg = warp >> 2;
     const long long ovox = (long long)a.od[0] * a.od[1] * a.od[2];
     const int N = a.N, npiece = N / 16;
@@ -590,9 +592,6 @@ static int cs_plan(const TcConv& c, const TcIO& io, const CsPack& p, CsPlan& pl)
   for (int c0 : cand)
     for (int c1 : cand)
       for (int c2 : cand) {
-        if ((c0 > a.rd[0] && c0 != cand[0]) || (c1 > a.rd[1] && c1 != cand[0]) || (c2 > a.rd[2] && c2 != cand[0])) {
-          // candidates above the extent collapse to the extent itself: visit that once (through the smallest such)
-        }
         const int t[3] = {std::min(c0, a.rd[0]), std::min(c1, a.rd[1]), std::min(c2, a.rd[2])};
         const int H[3] = {t[0] + addH[0], t[1] + addH[1], t[2] + addH[2]};
         const int P = round_up(H[0] * H[1] * H[2], 8);
@@ -615,12 +614,10 @@ static int cs_plan(const TcConv& c, const TcIO& io, const CsPack& p, CsPlan& pl)
           const int nbuf = cols <= 256 ? 2 : 1;
           const long long units = (long long)ceil_div(io.n, G) * nbricks * p.ncoblk;
           const double rounds = (double)((units + nsm - 1) / nsm);
-          const double mma = (double)G * ntl * p.nkc * p.ntap * mma_clk(a.NB) / std::min(kIssuers, G * ntl) * 1.0;
-          // the tensor pipe is shared by the two issuers: a unit's MMAs take at least their summed pipe time
+          // the tensor pipe is shared by the issuers: a unit's MMAs take at least their summed pipe time
           const double pipe = (double)G * ntl * p.nkc * p.ntap * mma_clk(a.NB);
           const double epi = (double)ceil_div(G * ntl, 2) * a.ncls * (a.N / 16) * 1300.0;
           const double load = ((double)a_stage * p.nkc + (double)p.nkc * p.ntap * a.NB * 32) / 24.0;
-          (void)mma;
           const double unit = nbuf == 2 ? std::max(std::max(pipe, epi), load) + 1500.0 : std::max(pipe, load) + epi + 1500.0;
           const double cost = rounds * unit;
           if (cost < best) best = cost, bt[0] = t[0], bt[1] = t[1], bt[2] = t[2], bG = G, bst = ast;
