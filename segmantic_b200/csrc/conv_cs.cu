@@ -603,6 +603,9 @@ static int cs_plan(const TcConv& c, const TcIO& io, const CsPack& p, CsPlan& pl)
         const long long nbricks = (long long)ceil_div(a.rd[0], t[0]) * ceil_div(a.rd[1], t[1]) * ceil_div(a.rd[2], t[2]);
         for (int G : gcand) {
           if (force_g && G != force_g) continue;
+          // Several windows per unit (G > 1) are implemented (shared weight stages for 2-4 small windows) but no
+          // launch of the benched or tested shapes ever selected them: opt-in through SGM_CS_G until they have run.
+          if (!force_g && G > 1) break;
           if (G > io.n) break;
           if (nbricks > 1 && G > 1) break;  // several windows per unit only when a window is a single brick
           const int cols = G * ntl * cols_tile;
