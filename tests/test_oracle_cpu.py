@@ -252,3 +252,73 @@ def test_oracle_tie_gap_follows_the_labels():
     inside = torch.isfinite(gap)
     assert int(inside.sum()) == logits.shape[1] * logits.shape[2] * logits.shape[3]   # the cropped grid, nothing else
     assert not lab[~inside].any()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Independent cross-checks (scipy: a third implementation that shares no code with torch or with this repo).  They do
+# not replace MONAI / ITK golden vectors -- the oracle stays "parity unpinned" against those libraries -- but they pin
+# the interior arithmetic of the restatements to an outside party.
+def test_itk_linear_interior_matches_scipy_map_coordinates():
+    """Linear interpolation at ITK's continuous indices == scipy.ndimage.map_coordinates(order=1) wherever all eight
+    neighbours exist (the borders are ITK-specific: clamped neighbours, [-0.5, n - 0.5) inside test)."""
+    from scipy import ndimage
+    rng = np.random.default_rng(5)
+    arr = rng.random((14, 11, 9)).astype(np.float32)
+    mov = oitk.Image(arr, (0.5, 0.6, 0.7), (1.0, -2.0, 0.5))
+    size, sp, org = (20, 13, 8), (0.31, 0.47, 0.73), (1.2, -1.8, 0.7)
+    out = oitk.resample_onto_grid(mov, size, sp, org, tuple(np.eye(3).flatten()), nearest=False).array
+    grids = np.meshgrid(*[np.arange(n, dtype=np.float64) for n in size], indexing="ij")
+    coords = [(g * sp[a] + org[a] - mov.origin[a]) / mov.spacing[a] for a, g in enumerate(grids)]
+    ref = ndimage.map_coordinates(arr.astype(np.float64), coords, order=1, mode="nearest")
+    interior = np.ones(size, dtype=bool)
+    for a in range(3):
+        interior &= (coords[a] >= 0.0) & (coords[a] <= arr.shape[a] - 1.0)
+    assert interior.mean() > 0.5
+    assert np.allclose(out[interior], ref[interior], rtol=0, atol=2e-6)
+
+
+def test_itk_nearest_matches_scipy_away_from_half_way_points():
+    """Nearest neighbour: floor(c + 0.5) (ITK rounds half UP) == scipy's order-0 lookup except exactly half-way between
+    two voxels, where the rounding rules may differ."""
+    from scipy import ndimage
+    rng = np.random.default_rng(6)
+    arr = (rng.random((12, 10, 7)) * 200).astype(np.uint8)
+    mov = oitk.Image(arr, (1.0, 1.0, 1.0), (0.0, 0.0, 0.0))
+    size, sp, org = (17, 14, 9), (0.7, 0.65, 0.8), (0.05, 0.1, 0.15)
+    out = oitk.resample_onto_grid(mov, size, sp, org, tuple(np.eye(3).flatten()), nearest=True).array
+    grids = np.meshgrid(*[np.arange(n, dtype=np.float64) for n in size], indexing="ij")
+    coords = [g * sp[a] + org[a] for a, g in enumerate(grids)]
+    ref = ndimage.map_coordinates(arr, coords, order=0, mode="nearest")
+    ok = np.ones(size, dtype=bool)
+    for a in range(3):
+        frac = np.abs(coords[a] - np.floor(coords[a]) - 0.5)
+        ok &= (frac > 1e-9) & (coords[a] >= -0.5 + 1e-9) & (coords[a] < arr.shape[a] - 0.5 - 1e-9)
+    assert ok.mean() > 0.5
+    assert np.array_equal(out[ok], ref[ok])
+
+
+def test_spacing_resample_interior_matches_scipy():
+    """Spacingd's trilinear resample (F.grid_sample, align_corners=False, border padding, float64) against
+    scipy.ndimage.map_coordinates(order=1) at the voxel-centre coordinates the affine prescribes."""
+    from scipy import ndimage
+    g = torch.Generator().manual_seed(4)
+    img = torch.randn((1, 18, 16, 9), generator=g)
+    aff = np.diag([0.5, 0.5, 3.0, 1.0])
+    out, new_aff, rec = osp.spacing_forward(img, aff, (1.0, 1.0, 1.0))
+    xform = np.linalg.solve(aff, new_aff)          # output voxel index -> input voxel index
+    grids = np.meshgrid(*[np.arange(n, dtype=np.float64) for n in out.shape[1:]], indexing="ij")
+    coords = [xform[a, a] * grids[a] + xform[a, 3] for a in range(3)]
+    ref = ndimage.map_coordinates(img[0].double().numpy(), coords, order=1, mode="nearest")
+    assert np.allclose(out[0].numpy(), ref, rtol=0, atol=1e-6)
+
+
+def test_gaussian_importance_map_matches_scipy_window():
+    """compute_importance_map(mode="gaussian", sigma_scale=0.125): the separable window exp(-x^2 / (2 sigma^2)) with
+    sigma = 0.125 * n, x centred -- scipy.signal.windows.gaussian is the same window."""
+    from scipy.signal import windows
+    for roi in ((96, 96, 96), (32, 48, 64)):
+        imap = osw.importance_map(roi, "gaussian", 0.125).numpy()
+        w = [windows.gaussian(n, 0.125 * n).astype(np.float32) for n in roi]
+        ref = w[0][:, None, None] * w[1][None, :, None] * w[2][None, None, :]
+        ref = np.maximum(ref, max(float(ref.min()), 1e-3))
+        assert np.allclose(imap, ref, rtol=2e-6, atol=0)
