@@ -6,14 +6,14 @@ prediction path, so code written against the reference keeps its imports --
     from segmantic.commands.monai_unet_cli import main
 
 Only the modules the drop-in implements are aliased (``seg.monai_unet``, ``seg.utils``, ``seg.evaluation``,
-``seg.transforms``, ``image.processing``, ``image.labels``, ``image.utils``, ``commands.monai_unet_cli``); anything
+``seg.transforms``, ``image.processing``, ``image.labels``, ``commands.monai_unet_cli``); anything
 else of the reference (training, datasets, plotting ...) raises ImportError as an absent module would.
 """
 import importlib
 import sys
 
 _ALIASED = ("seg", "seg.monai_unet", "seg.utils", "seg.evaluation", "seg.transforms", "image", "image.processing",
-            "image.labels", "image.utils", "commands", "commands.monai_unet_cli")
+            "image.labels", "commands", "commands.monai_unet_cli")
 
 for _name in _ALIASED:
     _mod = importlib.import_module("segmantic_b200." + _name)

@@ -301,15 +301,6 @@ def test_reference_label_fixtures(tmp_path):
     assert omap == {"Background": 0, "Bone": 1, "Other_tissue": 2} and i2o.tolist() == [0, 1, 2, 2]
 
 
-def test_reference_image_order_fixture():
-    """tests/image/test_image_order.py of the reference replayed: a view (no copy) with the axes reversed."""
-    from segmantic_b200.image.utils import array_view_reverse_ordering
-    im3d = np.random.default_rng(0).random((12, 13, 14))
-    im3d_f = array_view_reverse_ordering(im3d)
-    assert im3d_f.flags.owndata is False and im3d.shape == im3d_f.shape[::-1]
-    assert all(im3d[k, j, i] == im3d_f[i, j, k] for k in range(12) for j in range(13) for i in range(14))
-
-
 def test_segmantic_import_shim_and_console_script():
     """`segmantic.*` imports of the reference resolve to the drop-in, and pyproject.toml declares the reference's
     console script (`segmantic-unet`, /root/reference/pyproject.toml:64-65)."""
